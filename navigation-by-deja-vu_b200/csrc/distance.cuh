@@ -1,0 +1,361 @@
+// distance.cuh -- K2: batched glimpse-vs-library image difference with a fused
+// per-glimpse min/argmin.
+//
+// Replaces sads_hsv_metric (navsim/util.pyx:28-73) plus the per-heading max of
+// step_forward (navsim/NavBySceneFamiliarity.py:313): for every glimpse
+// g = (agent, heading) it finds the library view with the smallest image
+// difference.  With chem_weight == 0 (util.pyx:10 default) the metric is
+// sum |dV| / 255 on one uint8 plane, so the kernel works on the integer sum
+// (order-equivalent to the reference's FP64 sum whenever two sums differ;
+// equal sums are resolved in exact FP64 by the tie pass in step.cuh).
+//
+// Layout: glimpses gv [G][Ppad], library lv [N][Ppad], uint8, rows 16-B aligned,
+// pad bytes zero.  A CTA owns a TG x TN (glimpse x view) tile; both operand
+// tiles are streamed into shared memory in K-chunks of KC = 16*CPR bytes with
+// a cp.async multi-stage ring (XOR-swizzled 16-B chunks when CPR is even so the
+// row-strided LDS.128 reads are bank-conflict free); every thread accumulates
+// an MG x MV register tile with byte-SIMD VABSDIFF4+accumulate (nvb_sad4: four
+// pixel differences per instruction, SASS VABSDIFF4.U8.ACC).  The epilogue folds (sum, view) into one
+// packed key and reduces min over views with warp shuffles and one 64-bit
+// atomicMin per glimpse row.
+//
+// key = (score << idx_bits) | view_index     (lower is more familiar)
+#pragma once
+#include "common.cuh"
+
+struct DistArgs {
+    const uint8_t *gv, *gh, *gs;  // glimpses [G][Ppad]
+    const uint8_t *lv, *lh, *ls;  // library  [N][Ppad]
+    int G, N, Ppad;
+    int nk;                       // K-chunks per row
+    int n_vt, vt_per_split;       // view tiles, view tiles per blockIdx.y
+    long long view_offset;        // global index of local view 0 (library shards)
+    unsigned long long *keys;     // [G], pre-set to ~0
+    double cw;
+    int idx_bits;
+};
+
+#define NVB_DIST_THREADS 256
+
+__device__ __forceinline__ void nvb_cp_async16(void *dst, const void *src, int src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(nvb_smem_u32(dst)), "l"(src),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void nvb_cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void nvb_cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// swizzle of the 16-B chunk index for a row of CPR chunks
+template <int CPR>
+__device__ __forceinline__ int nvb_swz(int row)
+{
+    if (CPR == 8) return row & 7;          // 128-B rows: chunk ^= row[0:3]
+    if (CPR == 4) return (row >> 1) & 3;   // 64-B rows
+    if (CPR == 2) return (row >> 2) & 1;   // 32-B rows
+    return 0;                              // odd chunk counts are conflict free as they are
+}
+
+template <int TY, int MG, int MV, int CPR, int STAGES>
+struct DistCfg {
+    static constexpr int TX = NVB_DIST_THREADS / TY;
+    static constexpr int TG = TY * MG;
+    static constexpr int TN = TX * MV;
+    static constexpr int KC = 16 * CPR;
+    static constexpr int STAGE_BYTES = (TG + TN) * KC;
+    static constexpr int SMEM = STAGE_BYTES * STAGES;
+};
+
+template <int TY, int MG, int MV, int CPR, int STAGES>
+__global__ void __launch_bounds__(NVB_DIST_THREADS, 2)
+k2_sad_v(DistArgs a)
+{
+    using C = DistCfg<TY, MG, MV, CPR, STAGES>;
+    constexpr int TX = C::TX, TG = C::TG, TN = C::TN, KC = C::KC;
+    constexpr int LOGMV = (MV == 1) ? 0 : (MV == 2) ? 1 : (MV == 4) ? 2 : 3;
+    static_assert(MV == 1 || MV == 2 || MV == 4 || MV == 8, "MV must be a power of two <= 8");
+    extern __shared__ __align__(1024) uint8_t smem_k2[];
+    uint8_t *smem = smem_k2;
+
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    const int g0 = blockIdx.x * TG;
+    const int vt0 = blockIdx.y * a.vt_per_split;
+    const int vt1 = min(vt0 + a.vt_per_split, a.n_vt);
+    const int total = (vt1 - vt0) * a.nk;
+    if (total <= 0) return;
+
+    auto load_stage = [&](int it) {
+        const int vt = vt0 + it / a.nk, kc = it - (it / a.nk) * a.nk;
+        uint8_t *st = smem + (it % STAGES) * C::STAGE_BYTES;
+        const int kbyte = kc * KC;
+        for (int q = tid; q < (TG + TN) * CPR; q += NVB_DIST_THREADS) {
+            const int row = q / CPR, c = q - row * CPR;
+            const uint8_t *src;
+            int ok;
+            if (row < TG) {
+                const int g = g0 + row;
+                ok = (g < a.G) && (kbyte + 16 * c < a.Ppad);
+                src = a.gv + (size_t)(ok ? g : 0) * a.Ppad + (ok ? kbyte + 16 * c : 0);
+            } else {
+                const int v = vt * TN + (row - TG);
+                ok = (v < a.N) && (kbyte + 16 * c < a.Ppad);
+                src = a.lv + (size_t)(ok ? v : 0) * a.Ppad + (ok ? kbyte + 16 * c : 0);
+            }
+            const int r = (row < TG) ? row : row - TG;
+            uint8_t *dst = st + (row < TG ? 0 : TG * KC) + r * KC + 16 * (c ^ nvb_swz<CPR>(r));
+            nvb_cp_async16(dst, src, ok ? 16 : 0);
+        }
+    };
+
+    uint32_t acc[MG][MV];
+#pragma unroll
+    for (int i = 0; i < MG; i++)
+#pragma unroll
+        for (int j = 0; j < MV; j++) acc[i][j] = 0;
+    uint32_t best[MG];
+    int best_vt[MG];
+#pragma unroll
+    for (int i = 0; i < MG; i++) { best[i] = 0xFFFFFFFFu; best_vt[i] = 0; }
+
+    // per-thread row bases and swizzle terms
+    int goff[MG], gsw[MG], voff[MV], vsw[MV];
+#pragma unroll
+    for (int i = 0; i < MG; i++) { int r = ty + TY * i; goff[i] = r * KC; gsw[i] = nvb_swz<CPR>(r) << 4; }
+#pragma unroll
+    for (int j = 0; j < MV; j++) { int r = tx + TX * j; voff[j] = TG * KC + r * KC; vsw[j] = nvb_swz<CPR>(r) << 4; }
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < total) load_stage(s);
+        nvb_cp_async_commit();
+    }
+
+    for (int it = 0; it < total; it++) {
+        nvb_cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (it + STAGES - 1 < total) load_stage(it + STAGES - 1);
+        nvb_cp_async_commit();
+
+        const uint8_t *st = smem + (it % STAGES) * C::STAGE_BYTES;
+#pragma unroll(CPR <= 5 ? CPR : 1)
+        for (int c = 0; c < CPR; c++) {
+            uint4 av[MG];
+#pragma unroll
+            for (int i = 0; i < MG; i++)
+                av[i] = *reinterpret_cast<const uint4 *>(st + goff[i] + ((c << 4) ^ gsw[i]));
+#pragma unroll
+            for (int j = 0; j < MV; j++) {
+                const uint4 b = *reinterpret_cast<const uint4 *>(st + voff[j] + ((c << 4) ^ vsw[j]));
+#pragma unroll
+                for (int i = 0; i < MG; i++) {
+                    uint32_t s = acc[i][j];
+                    s = nvb_sad4(av[i].x, b.x, s);
+                    s = nvb_sad4(av[i].y, b.y, s);
+                    s = nvb_sad4(av[i].z, b.z, s);
+                    s = nvb_sad4(av[i].w, b.w, s);
+                    acc[i][j] = s;
+                }
+            }
+        }
+
+        const int kc = it % a.nk;
+        if (kc == a.nk - 1) {
+            const int vt = vt0 + it / a.nk;
+            const bool edge = (vt + 1) * TN > a.N;
+#pragma unroll
+            for (int i = 0; i < MG; i++) {
+                uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+                for (int j = 0; j < MV; j++) {
+                    uint32_t k = (acc[i][j] << LOGMV) | (uint32_t)j;
+                    if (edge && vt * TN + tx + TX * j >= a.N) k = 0xFFFFFFFFu;
+                    m = min(m, k);
+                    acc[i][j] = 0;
+                }
+                // strict < on the sum alone: an equal sum in a later tile has a higher view index
+                if ((m >> LOGMV) < (best[i] >> LOGMV)) { best[i] = m; best_vt[i] = vt; }
+            }
+        }
+    }
+
+    // (sum, view) -> 64-bit keys; min over the TX threads of a glimpse row
+    constexpr int RW = (TX < 32) ? TX : 32;
+#pragma unroll
+    for (int i = 0; i < MG; i++) {
+        unsigned long long key = NVB_KEY_NONE;
+        if (best[i] != 0xFFFFFFFFu) {
+            const unsigned long long sum = best[i] >> LOGMV;
+            const unsigned long long v =
+                (unsigned long long)(a.view_offset + (long long)best_vt[i] * TN + tx + TX * (int)(best[i] & (MV - 1)));
+            key = (sum << a.idx_bits) | v;
+        }
+#pragma unroll
+        for (int o = RW / 2; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+            key = (other < key) ? other : key;
+        }
+        const int g = g0 + ty + TY * i;
+        if ((tx % RW) == 0 && g < a.G && key != NVB_KEY_NONE) atomicMin(a.keys + g, key);
+    }
+}
+
+// ---- chem_weight > 0: hue/saturation branch + V, three planes ----------------
+// X = (Hq == Hn) ? |Sq - Sn| : Sq + Sn   (util.pyx:48-56), V = |Vq - Vn| (:69);
+// score = floor(4096 * (cw * 0.5 * sum X + (1 - cw) * sum V)): a fixed-point
+// surrogate of 255 * diff; candidates within one quantum of the minimum are
+// re-evaluated in exact FP64 by the tie pass.
+__device__ __forceinline__ unsigned long long nvb_hsv_score(uint32_t xs, uint32_t vs, double cw)
+{
+    double f = __dadd_rn(__dmul_rn(__dmul_rn((double)xs, 0.5), cw),
+                         __dmul_rn(__dsub_rn(1.0, cw), (double)vs));
+    return (unsigned long long)(f * 4096.0);
+}
+
+__device__ __forceinline__ void nvb_hsv_word(uint32_t qh, uint32_t qs, uint32_t qv, uint32_t fh,
+                                             uint32_t fs, uint32_t fv, uint32_t &xs, uint32_t &vs)
+{
+    const uint32_t eq = __vcmpeq4(qh, fh);          // 0xFF where hues match
+    xs = nvb_sad4(qs & eq, fs & eq, xs);            // |Sq - Sn| where equal
+    xs = nvb_sad4(qs & ~eq, 0u, xs);                // Sq + Sn where different
+    xs = nvb_sad4(fs & ~eq, 0u, xs);
+    vs = nvb_sad4(qv, fv, vs);
+}
+
+#define NVB_HSV_TG 8
+#define NVB_HSV_THREADS 128
+
+// one thread per view, NVB_HSV_TG glimpses per CTA held in shared memory
+__global__ void __launch_bounds__(NVB_HSV_THREADS)
+k2_sad_hsv(DistArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_hsv[];   // [3][TG][Ppad]
+    uint8_t *smem = smem_hsv;
+    const int g0 = blockIdx.x * NVB_HSV_TG;
+    const int tid = threadIdx.x;
+    const int words = a.Ppad / 4;
+    uint32_t *sm = reinterpret_cast<uint32_t *>(smem);
+    for (int q = tid; q < 3 * NVB_HSV_TG * words; q += NVB_HSV_THREADS) {
+        const int pl = q / (NVB_HSV_TG * words), r = (q / words) % NVB_HSV_TG, wd = q % words;
+        const uint8_t *src = (pl == 0) ? a.gh : (pl == 1) ? a.gs : a.gv;
+        const int g = g0 + r;
+        sm[q] = (g < a.G) ? reinterpret_cast<const uint32_t *>(src + (size_t)g * a.Ppad)[wd] : 0u;
+    }
+    __syncthreads();
+    const uint32_t *qh = sm, *qs = sm + NVB_HSV_TG * words, *qv = sm + 2 * NVB_HSV_TG * words;
+
+    const int v0 = blockIdx.y * a.vt_per_split * NVB_HSV_THREADS;
+    const int v1 = min(v0 + a.vt_per_split * NVB_HSV_THREADS, a.N);
+    unsigned long long best[NVB_HSV_TG];
+#pragma unroll
+    for (int i = 0; i < NVB_HSV_TG; i++) best[i] = NVB_KEY_NONE;
+
+    for (int v = v0 + tid; v < v1; v += NVB_HSV_THREADS) {
+        uint32_t xs[NVB_HSV_TG], vs[NVB_HSV_TG];
+#pragma unroll
+        for (int i = 0; i < NVB_HSV_TG; i++) { xs[i] = 0; vs[i] = 0; }
+        const uint32_t *fh = reinterpret_cast<const uint32_t *>(a.lh + (size_t)v * a.Ppad);
+        const uint32_t *fs = reinterpret_cast<const uint32_t *>(a.ls + (size_t)v * a.Ppad);
+        const uint32_t *fv = reinterpret_cast<const uint32_t *>(a.lv + (size_t)v * a.Ppad);
+        for (int wd = 0; wd < words; wd++) {
+            const uint32_t h = __ldg(fh + wd), s = __ldg(fs + wd), vv = __ldg(fv + wd);
+#pragma unroll
+            for (int i = 0; i < NVB_HSV_TG; i++)
+                nvb_hsv_word(qh[i * words + wd], qs[i * words + wd], qv[i * words + wd], h, s, vv,
+                             xs[i], vs[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < NVB_HSV_TG; i++) {
+            const unsigned long long key = (nvb_hsv_score(xs[i], vs[i], a.cw) << a.idx_bits) |
+                                           (unsigned long long)(a.view_offset + v);
+            best[i] = (key < best[i]) ? key : best[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NVB_HSV_TG; i++) {
+        unsigned long long key = best[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+            key = (other < key) ? other : key;
+        }
+        const int g = g0 + i;
+        if ((tid & 31) == 0 && g < a.G && key != NVB_KEY_NONE) atomicMin(a.keys + g, key);
+    }
+}
+
+// ---- exact FP64 difference of one (glimpse, view) pair -----------------------
+// The literal operation sequence of util.pyx:48-72 (no FMA contraction), so
+// that fam = H*W - diff is bit-identical to the reference.  q*/f* are rows of
+// the planar glimpse / library arrays; div255 = {k / 255.} for k in 0..255.
+__device__ __forceinline__ double nvb_exact_diff(const uint8_t *qh, const uint8_t *qs,
+                                                 const uint8_t *qv, const uint8_t *fh,
+                                                 const uint8_t *fs, const uint8_t *fv, int P,
+                                                 double cw, const double *div255)
+{
+    double diff = 0.0;
+    if (cw == 0.0) {
+        // thispx = X*0.5*0 (= +0) + 1*|dV|, then / 255.  (util.pyx:59-72)
+        for (int p = 0; p < P; p++) {
+            int d = (int)qv[p] - (int)fv[p];
+            d = d < 0 ? -d : d;
+            diff = __dadd_rn(diff, div255[d]);
+        }
+    } else {
+        const double omc = __dsub_rn(1.0, cw);
+        for (int p = 0; p < P; p++) {
+            int sq = qs[p], sn = fs[p];
+            int x = (qh[p] == fh[p]) ? (sq > sn ? sq - sn : sn - sq) : (sq + sn);
+            int d = (int)qv[p] - (int)fv[p];
+            d = d < 0 ? -d : d;
+            double t = (double)x;
+            t = __dmul_rn(t, 0.5);
+            t = __dmul_rn(t, cw);
+            t = __dadd_rn(t, __dmul_rn(omc, (double)d));
+            t = __ddiv_rn(t, 255.0);
+            diff = __dadd_rn(diff, t);
+        }
+    }
+    return diff;
+}
+
+// A5 for the single-call API: fam [G][N] = H*W - diff, one thread per pair.
+__global__ void k_familiarity_exact(DistArgs a, int P, double maxfam, const double *div255,
+                                    double *fam)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)a.G * a.N) return;
+    const int g = (int)(i / a.N), n = (int)(i - (long long)g * a.N);
+    const size_t qo = (size_t)g * a.Ppad, fo = (size_t)n * a.Ppad;
+    const double d = nvb_exact_diff(a.gh + qo, a.gs + qo, a.gv + qo, a.lh + fo, a.ls + fo,
+                                    a.lv + fo, P, a.cw, div255);
+    fam[i] = __dsub_rn(maxfam, d);
+}
+
+// Register-resident VABSDIFF4+accumulate issue-rate probe (bench.py's ALU
+// roofline denominator).  Each thread runs `iters` x 32 dependent-free SADs.
+__global__ void k_probe_sad(int iters, uint32_t seed, uint32_t *sink)
+{
+    uint32_t acc[8], a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc[i] = i; a[i] = seed * (i + 1) + threadIdx.x; }
+#pragma unroll
+    for (int r = 0; r < 4; r++) b[r] = seed * 3u + blockIdx.x + r * 0x01010101u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = nvb_sad4(a[i], b[r], acc[i]);
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += acc[i];
+    if (s == 0xDEADBEEFu) sink[0] = s;
+}

@@ -1,0 +1,1011 @@
+// engine.cu -- host side of the C ABI declared in include/navsim_b200.h.
+//
+// One engine = one world (landscape + sensor + heading sweep + library) on one
+// B200 and one stream.  All device memory is owned here; Python (ctypes) and
+// torch only hand in host pointers, a stream handle and, for the view-sharded
+// mode, read the two reduction buffers through nvb_device_ptr().
+// There is no CPU fallback: without an sm_100 device nvb_engine_create fails.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/navsim_b200.h"
+#include "common.cuh"
+#include "distance.cuh"
+#include "sampler.cuh"
+#include "step.cuh"
+
+#define KEY_NONE NVB_KEY_NONE
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t _e = (call);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return fail(NVB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                               \
+    } while (0)
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                        const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                        const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct nvb_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    int64_t launches = 0;
+    // landscape
+    uint8_t *d_land = nullptr;
+    int rows = 0, cols = 0, pitch = 0;
+    CUtensorMap tmap;
+    // sensor
+    bool have_sensor = false;
+    int W = 0, H = 0, pw = 0, ph = 0, P = 0, Ppad = 0, cpr = 0, nk = 0;
+    int mask_lo = 0, mask_hi = 0;
+    int R = 0, BW = 0, BH = 0;
+    uint8_t *d_lut = nullptr;
+    double *d_div255 = nullptr;
+    // saccade
+    int A = 0;
+    double *d_offsets = nullptr;
+    // nav params
+    double step_size = 1.0, max_dist = INFINITY, thf = 2.0, cvf = 0.8, cw = 0.0;
+    // library
+    int N = 0;
+    uint8_t *d_lh = nullptr, *d_ls = nullptr, *d_lv = nullptr;
+    double *d_path = nullptr;
+    int n_path = 0;
+    long long view_offset = 0, n_total = 0;
+    // glimpse buffers
+    long long Gcap = 0;
+    uint8_t *d_gh = nullptr, *d_gs = nullptr, *d_gv = nullptr;
+    unsigned long long *d_keys = nullptr, *d_exact = nullptr;
+    int *d_tie_count = nullptr;
+    int2 *d_tie_items = nullptr;
+    unsigned long long *d_tie_thr = nullptr;
+    // agents
+    int B = 0;
+    AgentState ag{};
+    int *d_step = nullptr;
+    int steps_done = 0;
+    // log
+    int log_cap = 0, log_A = 0;
+    int16_t *log_best = nullptr;
+    double *log_pose = nullptr, *log_sfam = nullptr, *log_afam = nullptr;
+};
+
+// ---------------------------------------------------------------------------
+static void free_dev(void *p)
+{
+    if (p) cudaFree(p);
+}
+
+template <typename T>
+static int alloc_dev(T **p, size_t n)
+{
+    free_dev(*p);
+    *p = nullptr;
+    if (n == 0) n = 1;
+    CK(cudaMalloc((void **)p, n * sizeof(T)));
+    return NVB_OK;
+}
+
+static NvbWorld make_world(const nvb_engine *e)
+{
+    NvbWorld w;
+    w.land = e->d_land;
+    w.rows = e->rows;
+    w.cols = e->cols;
+    w.pitch = e->pitch;
+    w.plane_stride = (long long)e->pitch * e->rows;
+    w.W = e->W; w.H = e->H; w.pw = e->pw; w.ph = e->ph;
+    w.P = e->P; w.Ppad = e->Ppad;
+    w.Wpx = e->W * e->pw; w.Hpx = e->H * e->ph;
+    w.mask_lo = e->mask_lo; w.mask_hi = e->mask_hi;
+    w.r = (double)(w.Wpx > w.Hpx ? w.Wpx : w.Hpx) / 2.0;
+    w.R = e->R; w.BW = e->BW; w.BH = e->BH;
+    w.lut = e->d_lut;
+    return w;
+}
+
+static int rebuild_tmap(nvb_engine *e)
+{
+    memset(&e->tmap, 0, sizeof e->tmap);
+    e->R = 0;
+    if (!e->d_land || !e->have_sensor) return NVB_OK;
+    const double hw = 0.5 * e->W * e->pw, hh = 0.5 * e->H * e->ph;
+    const int R = (int)ceil(sqrt(hw * hw + hh * hh)) + 1;
+    const int BH = 2 * R + 2, BW = nvb_round_up(2 * R + 2, 16);
+    if (BW > 256 || BH > 256) return NVB_OK;   // window does not fit a TMA box: gather from global
+    if (nvb_sampler_smem(BW, BH, 3, e->A > 0 ? e->A : 1) > 200 * 1024) return NVB_OK;
+    static PFN_tmapEncodeTiled encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess)
+            return fail(NVB_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+        encode = (PFN_tmapEncodeTiled)fn;
+    }
+    cuuint64_t gdim[3] = {(cuuint64_t)e->cols, (cuuint64_t)e->rows, 3};
+    cuuint64_t gstride[2] = {(cuuint64_t)e->pitch, (cuuint64_t)e->pitch * (cuuint64_t)e->rows};
+    cuuint32_t box[3] = {(cuuint32_t)BW, (cuuint32_t)BH, 1};
+    cuuint32_t estride[3] = {1, 1, 1};
+    CUresult r = encode(&e->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, e->d_land, gdim, gstride, box,
+                        estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NVB_E_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+    e->R = R; e->BW = BW; e->BH = BH;
+    return NVB_OK;
+}
+
+static int ensure_glimpse_cap(nvb_engine *e, long long G)
+{
+    if (G <= e->Gcap) return NVB_OK;
+    int rc;
+    const size_t bytes = (size_t)G * e->Ppad;
+    if ((rc = alloc_dev(&e->d_gh, bytes))) return rc;
+    if ((rc = alloc_dev(&e->d_gs, bytes))) return rc;
+    if ((rc = alloc_dev(&e->d_gv, bytes))) return rc;
+    CK(cudaMemsetAsync(e->d_gh, 0, bytes, e->stream));
+    CK(cudaMemsetAsync(e->d_gs, 0, bytes, e->stream));
+    CK(cudaMemsetAsync(e->d_gv, 0, bytes, e->stream));
+    if ((rc = alloc_dev(&e->d_keys, (size_t)G))) return rc;
+    if ((rc = alloc_dev(&e->d_exact, (size_t)G))) return rc;
+    if ((rc = alloc_dev(&e->d_tie_items, (size_t)G))) return rc;
+    if ((rc = alloc_dev(&e->d_tie_thr, (size_t)G))) return rc;
+    e->Gcap = G;
+    return NVB_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" const char *nvb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *nvb_version(void) { return "navsim_b200 0.1 (sm_100a)"; }
+
+extern "C" int nvb_engine_create(int device, void *stream, nvb_engine **out)
+{
+    if (!out) return fail(NVB_E_INVALID, "out is NULL");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(NVB_E_NO_DEVICE, "no CUDA device visible; the engine has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(NVB_E_INVALID, "device %d out of range", device);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(NVB_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    CK(cudaSetDevice(device));
+    nvb_engine *e = new nvb_engine();
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    memset(&e->tmap, 0, sizeof e->tmap);
+    if (stream) {
+        e->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete e;
+            return fail(NVB_E_CUDA, "cudaStreamCreate failed");
+        }
+        e->own_stream = true;
+    }
+    double div[256];
+    for (int k = 0; k < 256; k++) div[k] = (double)k / 255.;
+    int rc = alloc_dev(&e->d_div255, 256);
+    if (rc) { delete e; return rc; }
+    cudaMemcpy(e->d_div255, div, sizeof div, cudaMemcpyHostToDevice);
+    alloc_dev(&e->d_step, 1);
+    alloc_dev(&e->d_tie_count, 1);
+    alloc_dev(&e->d_lut, 768);
+    *out = e;
+    return NVB_OK;
+}
+
+extern "C" void nvb_engine_destroy(nvb_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    void *ptrs[] = {e->d_land, e->d_lut, e->d_div255, e->d_offsets, e->d_lh, e->d_ls, e->d_lv,
+                    e->d_path, e->d_gh, e->d_gs, e->d_gv, e->d_keys, e->d_exact, e->d_tie_count,
+                    e->d_tie_items, e->d_tie_thr, e->ag.poses, e->ag.status, e->ag.completed,
+                    e->ag.budget, e->ag.nav_frames, e->ag.err_sum, e->ag.err_n, e->ag.coverage,
+                    e->ag.stepped, e->d_step, e->log_best, e->log_pose, e->log_sfam, e->log_afam};
+    for (void *p : ptrs) free_dev(p);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int nvb_sync(nvb_engine *e)
+{
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    return NVB_OK;
+}
+
+extern "C" int64_t nvb_launch_count(nvb_engine *e) { return e->launches; }
+
+extern "C" int nvb_set_landscape(nvb_engine *e, const uint8_t *hsv, int rows, int cols,
+                                 ptrdiff_t s_row, ptrdiff_t s_col, ptrdiff_t s_chan)
+{
+    if (!hsv || rows <= 0 || cols <= 0) return fail(NVB_E_INVALID, "bad landscape");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    const int pitch = nvb_round_up(cols, 16);
+    std::vector<uint8_t> planar((size_t)3 * rows * pitch, 0);
+    for (int ch = 0; ch < 3; ch++)
+        for (int y = 0; y < rows; y++) {
+            uint8_t *dst = planar.data() + ((size_t)ch * rows + y) * pitch;
+            const uint8_t *src = hsv + (ptrdiff_t)y * s_row + (ptrdiff_t)ch * s_chan;
+            for (int x = 0; x < cols; x++) dst[x] = src[(ptrdiff_t)x * s_col];
+        }
+    int rc = alloc_dev(&e->d_land, planar.size());
+    if (rc) return rc;
+    CK(cudaMemcpy(e->d_land, planar.data(), planar.size(), cudaMemcpyHostToDevice));
+    e->rows = rows; e->cols = cols; e->pitch = pitch;
+    return rebuild_tmap(e);
+}
+
+extern "C" int nvb_set_sensor(nvb_engine *e, int W, int H, int pw, int ph, const uint8_t *lut,
+                              int mask_middle_n)
+{
+    if (W <= 0 || H <= 0 || pw <= 0 || ph <= 0 || !lut) return fail(NVB_E_INVALID, "bad sensor");
+    if ((W * pw) % 2 || (H * ph) % 2)
+        return fail(NVB_E_INVALID, "sensor footprint must be even (NavBySceneFamiliarity.py:93)");
+    if (pw * ph > NVB_MAX_BLOCK_PX)
+        return fail(NVB_E_INVALID, "sensor pixel of %dx%d landscape pixels exceeds %d", pw, ph,
+                    NVB_MAX_BLOCK_PX);
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    e->W = W; e->H = H; e->pw = pw; e->ph = ph;
+    e->P = W * H;
+    int chunks = nvb_round_up(e->P, 16) / 16;
+    if (chunks >= 8) {
+        e->cpr = 8;
+        e->nk = (chunks + 7) / 8;
+    } else {
+        if (chunks % 2 == 0 && chunks != 2 && chunks != 4) chunks += 1;   // 6 -> 7
+        e->cpr = chunks;
+        e->nk = 1;
+    }
+    e->Ppad = chunks * 16;
+    // out[:, r1-m : r1+m] = 0 with Python slice semantics (NavBySceneFamiliarity.py:189-190)
+    long lo = W / 2 - mask_middle_n, hi = W / 2 + mask_middle_n;
+    if (lo < 0) { lo += W; if (lo < 0) lo = 0; }
+    if (hi < 0) { hi += W; if (hi < 0) hi = 0; }
+    if (hi > W) hi = W;
+    if (lo > W) lo = W;
+    e->mask_lo = (int)lo; e->mask_hi = (int)hi;
+    CK(cudaMemcpy(e->d_lut, lut, 768, cudaMemcpyHostToDevice));
+    e->have_sensor = true;
+    // sensor change invalidates library and glimpse buffers
+    e->N = 0; e->n_path = 0; e->Gcap = 0; e->B = 0;
+    return rebuild_tmap(e);
+}
+
+extern "C" int nvb_set_saccade(nvb_engine *e, int A, const double *offs)
+{
+    if (A <= 0 || A > 32767 || !offs) return fail(NVB_E_INVALID, "bad saccade");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    int rc = alloc_dev(&e->d_offsets, (size_t)A);
+    if (rc) return rc;
+    CK(cudaMemcpy(e->d_offsets, offs, sizeof(double) * A, cudaMemcpyHostToDevice));
+    e->A = A;
+    e->B = 0;
+    return rebuild_tmap(e);
+}
+
+extern "C" int nvb_set_nav_params(nvb_engine *e, double step_size, double max_dist, double thf,
+                                  double cvf, double cw)
+{
+    if (!(cw >= 0.0 && cw <= 1.0)) return fail(NVB_E_INVALID, "chem_weight must be in [0, 1]");
+    e->step_size = step_size; e->max_dist = max_dist; e->thf = thf; e->cvf = cvf; e->cw = cw;
+    return NVB_OK;
+}
+
+// ---------------------------------------------------------------------------
+static int launch_sampler(nvb_engine *e, const SamplerArgs &sa, int nblocks)
+{
+    const int nplanes = sa.need_hs ? 3 : 1;
+    const size_t smem = e->R > 0 ? nvb_sampler_smem(e->BW, e->BH, nplanes, sa.A)
+                                 : nvb_sampler_smem(0, 0, 0, sa.A);
+    static size_t attr_set[64] = {0};
+    if (smem > attr_set[e->device & 63]) {
+        CK(cudaFuncSetAttribute(k1_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[e->device & 63] = smem;
+    }
+    k1_sample<<<nblocks, NVB_SAMPLER_THREADS, smem, e->stream>>>(e->tmap, sa);
+    e->launches++;
+    CK(cudaGetLastError());
+    return NVB_OK;
+}
+
+template <int TY, int MG, int MV, int CPR>
+static int launch_dist_cfg(nvb_engine *e, DistArgs da)
+{
+    constexpr int STAGES = 3;
+    using C = DistCfg<TY, MG, MV, CPR, STAGES>;
+    auto kern = k2_sad_v<TY, MG, MV, CPR, STAGES>;
+    static int occ_dev[64] = {0};
+    int &occ = occ_dev[e->device & 63];
+    if (occ == 0) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NVB_DIST_THREADS, C::SMEM));
+        if (occ < 1) occ = 1;
+    }
+    const int n_gt = (da.G + C::TG - 1) / C::TG;
+    const int n_vt = (da.N + C::TN - 1) / C::TN;
+    const long long slots = (long long)e->sm_count * occ;
+    // split the view tiles over blockIdx.y so that the grid fills whole waves
+    int best_s = 1;
+    long long best_cost = -1;
+    for (int s = 1; s <= n_vt; s++) {
+        const int per = (n_vt + s - 1) / s;
+        const int s_eff = (n_vt + per - 1) / per;
+        const long long waves = ((long long)n_gt * s_eff + slots - 1) / slots;
+        const long long cost = waves * per;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s_eff; }
+        if (s_eff < s) break;
+    }
+    da.n_vt = n_vt;
+    da.vt_per_split = (n_vt + best_s - 1) / best_s;
+    dim3 grid(n_gt, (n_vt + da.vt_per_split - 1) / da.vt_per_split);
+    kern<<<grid, NVB_DIST_THREADS, C::SMEM, e->stream>>>(da);
+    e->launches++;
+    CK(cudaGetLastError());
+    return NVB_OK;
+}
+
+template <int CPR>
+static int launch_dist_cpr(nvb_engine *e, const DistArgs &da)
+{
+    if (da.G <= 16) return launch_dist_cfg<1, 16, 2, CPR>(e, da);
+    if (da.G <= 64) return launch_dist_cfg<4, 8, 4, CPR>(e, da);
+    return launch_dist_cfg<16, 8, 8, CPR>(e, da);
+}
+
+// K2 over glimpses [0, G) of the engine's glimpse buffers; keys must be reset.
+static int launch_distance(nvb_engine *e, int G)
+{
+    DistArgs da;
+    da.gv = e->d_gv; da.gh = e->d_gh; da.gs = e->d_gs;
+    da.lv = e->d_lv; da.lh = e->d_lh; da.ls = e->d_ls;
+    da.G = G; da.N = e->N; da.Ppad = e->Ppad; da.nk = e->nk;
+    da.n_vt = 0; da.vt_per_split = 0;
+    da.view_offset = e->view_offset;
+    da.keys = e->d_keys;
+    da.cw = e->cw;
+    da.idx_bits = (e->cw == 0.0) ? 32 : 28;
+    if (e->cw != 0.0) {
+        const size_t smem = (size_t)3 * NVB_HSV_TG * e->Ppad;
+        static size_t attr_set[64] = {0};
+        if (smem > 48 * 1024 && smem > attr_set[e->device & 63]) {
+            CK(cudaFuncSetAttribute(k2_sad_hsv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[e->device & 63] = smem;
+        }
+        const int n_gt = (G + NVB_HSV_TG - 1) / NVB_HSV_TG;
+        const int n_vt = (e->N + NVB_HSV_THREADS - 1) / NVB_HSV_THREADS;
+        int splits = (int)((4LL * e->sm_count + n_gt - 1) / n_gt);
+        if (splits < 1) splits = 1;
+        if (splits > n_vt) splits = n_vt;
+        da.n_vt = n_vt;
+        da.vt_per_split = (n_vt + splits - 1) / splits;
+        dim3 grid(n_gt, (n_vt + da.vt_per_split - 1) / da.vt_per_split);
+        k2_sad_hsv<<<grid, NVB_HSV_THREADS, smem, e->stream>>>(da);
+        e->launches++;
+        CK(cudaGetLastError());
+        return NVB_OK;
+    }
+    switch (e->cpr) {
+    case 1: return launch_dist_cpr<1>(e, da);
+    case 2: return launch_dist_cpr<2>(e, da);
+    case 3: return launch_dist_cpr<3>(e, da);
+    case 4: return launch_dist_cpr<4>(e, da);
+    case 5: return launch_dist_cpr<5>(e, da);
+    case 7: return launch_dist_cpr<7>(e, da);
+    case 8: return launch_dist_cpr<8>(e, da);
+    }
+    return fail(NVB_E_INVALID, "unsupported chunk count %d", e->cpr);
+}
+
+__global__ void k_fill_u64(unsigned long long *p, long long n, unsigned long long v)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+static int fill_u64(nvb_engine *e, unsigned long long *p, long long n, unsigned long long v)
+{
+    if (n <= 0) return NVB_OK;
+    k_fill_u64<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(p, n, v);
+    e->launches++;
+    CK(cudaGetLastError());
+    return NVB_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int nvb_fill_sensor(nvb_engine *e, uint8_t *sensor, int Hpx, int Wpx, double x, double y,
+                               double c, double s)
+{
+    if (!e->d_land) return fail(NVB_E_INVALID, "no landscape");
+    CK(cudaSetDevice(e->device));
+    const size_t n = (size_t)Hpx * Wpx;
+    uint8_t *d_out = nullptr;
+    int *d_err = nullptr;
+    CK(cudaMalloc(&d_out, n * 3 + 16));
+    CK(cudaMalloc(&d_err, sizeof(int)));
+    CK(cudaMemsetAsync(d_err, 0, sizeof(int), e->stream));
+    NvbWorld w = make_world(e);
+    if (n) {
+        k_fill_sensor<<<(unsigned)((n + 127) / 128), 128, 0, e->stream>>>(w, Hpx, Wpx, x, y, c, s, d_out, d_err);
+        e->launches++;
+    }
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(sensor, d_out, n * 3, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d_out);
+    cudaFree(d_err);
+    return err ? NVB_INDEX_ERROR : NVB_OK;
+}
+
+extern "C" int nvb_downscale_chem(nvb_engine *e, const uint8_t *image, int R, int C, int fr, int fc,
+                                  uint8_t *out)
+{
+    if (fr <= 0 || fc <= 0 || R < 0 || C < 0) return fail(NVB_E_INVALID, "bad downscale arguments");
+    CK(cudaSetDevice(e->device));
+    const size_t nin = (size_t)R * C * 3, nout = (size_t)(R / fr) * (C / fc);
+    if (nout == 0) return NVB_OK;
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_in, nin));
+    CK(cudaMalloc(&d_out, nout * 3));
+    CK(cudaMemcpyAsync(d_in, image, nin, cudaMemcpyHostToDevice, e->stream));
+    k_downscale_chem<<<(unsigned)((nout + 127) / 128), 128, 0, e->stream>>>(d_in, R, C, fr, fc, d_out);
+    e->launches++;
+    CK(cudaMemcpyAsync(out, d_out, nout * 3, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return NVB_OK;
+}
+
+// pose-mode K1 into the given planes; status to d_status
+static int sample_poses(nvb_engine *e, const double *poses, const double *cs, int G, uint8_t *ph,
+                        uint8_t *ps, uint8_t *pv, int32_t *d_status)
+{
+    double *d_poses = nullptr, *d_cs = nullptr;
+    CK(cudaMalloc(&d_poses, sizeof(double) * 3 * G));
+    CK(cudaMemcpyAsync(d_poses, poses, sizeof(double) * 3 * G, cudaMemcpyHostToDevice, e->stream));
+    if (cs) {
+        CK(cudaMalloc(&d_cs, sizeof(double) * 2 * G));
+        CK(cudaMemcpyAsync(d_cs, cs, sizeof(double) * 2 * G, cudaMemcpyHostToDevice, e->stream));
+    }
+    SamplerArgs sa;
+    sa.w = make_world(e);
+    sa.poses = d_poses; sa.offsets = nullptr; sa.cs = d_cs;
+    sa.A = 1; sa.agent_mode = 0; sa.need_hs = 1;
+    sa.status = d_status; sa.completed = nullptr; sa.budget = nullptr;
+    sa.gv = pv; sa.gh = ph; sa.gs = ps;
+    sa.keys = nullptr;
+    int rc = launch_sampler(e, sa, G);
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d_poses);
+    if (d_cs) cudaFree(d_cs);
+    return rc;
+}
+
+extern "C" int nvb_glimpse_batch(nvb_engine *e, const double *poses, const double *cs, int G,
+                                 uint8_t *out, int32_t *status)
+{
+    if (!e->d_land || !e->have_sensor) return fail(NVB_E_INVALID, "landscape and sensor must be set");
+    if (G <= 0) return NVB_OK;
+    CK(cudaSetDevice(e->device));
+    int rc = ensure_glimpse_cap(e, G);
+    if (rc) return rc;
+    int32_t *d_status = nullptr;
+    uint8_t *d_out = nullptr;
+    CK(cudaMalloc(&d_status, sizeof(int32_t) * G));
+    CK(cudaMalloc(&d_out, (size_t)G * e->P * 3));
+    rc = sample_poses(e, poses, cs, G, e->d_gh, e->d_gs, e->d_gv, d_status);
+    if (!rc) {
+        const long long n = (long long)G * e->P;
+        k_planar_to_hsv<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->d_gh, e->d_gs, e->d_gv,
+                                                                           e->Ppad, e->P, G, d_out);
+        e->launches++;
+        CK(cudaMemcpyAsync(out, d_out, (size_t)n * 3, cudaMemcpyDeviceToHost, e->stream));
+        if (status)
+            CK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * G, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    cudaFree(d_status);
+    cudaFree(d_out);
+    return rc;
+}
+
+static int alloc_library(nvb_engine *e, int N)
+{
+    int rc;
+    const size_t bytes = (size_t)N * e->Ppad;
+    if ((rc = alloc_dev(&e->d_lh, bytes))) return rc;
+    if ((rc = alloc_dev(&e->d_ls, bytes))) return rc;
+    if ((rc = alloc_dev(&e->d_lv, bytes))) return rc;
+    CK(cudaMemsetAsync(e->d_lh, 0, bytes, e->stream));
+    CK(cudaMemsetAsync(e->d_ls, 0, bytes, e->stream));
+    CK(cudaMemsetAsync(e->d_lv, 0, bytes, e->stream));
+    e->N = N;
+    e->view_offset = 0;
+    e->n_total = N;
+    return NVB_OK;
+}
+
+static int set_path(nvb_engine *e, const double *path, int n)
+{
+    int rc = alloc_dev(&e->d_path, (size_t)2 * n);
+    if (rc) return rc;
+    CK(cudaMemcpy(e->d_path, path, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
+    e->n_path = n;
+    return NVB_OK;
+}
+
+extern "C" int nvb_library_build(nvb_engine *e, const double *path, const double *angles,
+                                 const double *cs, int N, int *bad_index)
+{
+    if (!e->d_land || !e->have_sensor) return fail(NVB_E_INVALID, "landscape and sensor must be set");
+    if (N <= 0 || !path || !angles) return fail(NVB_E_INVALID, "bad path");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    int rc = alloc_library(e, N);
+    if (rc) return rc;
+    std::vector<double> poses((size_t)3 * N);
+    for (int i = 0; i < N; i++) {
+        poses[3 * i] = path[2 * i];
+        poses[3 * i + 1] = path[2 * i + 1];
+        poses[3 * i + 2] = angles[i];
+    }
+    int32_t *d_status = nullptr;
+    CK(cudaMalloc(&d_status, sizeof(int32_t) * N));
+    rc = sample_poses(e, poses.data(), cs, N, e->d_lh, e->d_ls, e->d_lv, d_status);
+    std::vector<int32_t> st(N);
+    if (!rc) CK(cudaMemcpy(st.data(), d_status, sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
+    cudaFree(d_status);
+    if (rc) return rc;
+    for (int i = 0; i < N; i++)
+        if (st[i] != 0) {
+            if (bad_index) *bad_index = i;
+            e->N = 0;
+            return st[i];
+        }
+    e->B = 0;
+    return set_path(e, path, N);
+}
+
+extern "C" int nvb_library_upload(nvb_engine *e, const uint8_t *scenes, const double *path, int N)
+{
+    if (!e->have_sensor) return fail(NVB_E_INVALID, "sensor must be set");
+    if (N <= 0 || !scenes) return fail(NVB_E_INVALID, "bad library");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    int rc = alloc_library(e, N);
+    if (rc) return rc;
+    uint8_t *d_in = nullptr;
+    const long long n = (long long)N * e->P;
+    CK(cudaMalloc(&d_in, (size_t)n * 3));
+    CK(cudaMemcpyAsync(d_in, scenes, (size_t)n * 3, cudaMemcpyHostToDevice, e->stream));
+    k_hsv_to_planar<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(d_in, e->Ppad, e->P, N, e->d_lh,
+                                                                       e->d_ls, e->d_lv);
+    e->launches++;
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d_in);
+    e->B = 0;
+    if (path) return set_path(e, path, N);
+    e->n_path = 0;
+    return NVB_OK;
+}
+
+extern "C" int nvb_set_training_path(nvb_engine *e, const double *path, int n)
+{
+    if (!path || n <= 0) return fail(NVB_E_INVALID, "bad path");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    e->B = 0;   // coverage is sized by the path
+    return set_path(e, path, n);
+}
+
+extern "C" int nvb_library_download(nvb_engine *e, uint8_t *scenes)
+{
+    if (e->N <= 0) return fail(NVB_E_INVALID, "no library");
+    CK(cudaSetDevice(e->device));
+    uint8_t *d_out = nullptr;
+    const long long n = (long long)e->N * e->P;
+    CK(cudaMalloc(&d_out, (size_t)n * 3));
+    k_planar_to_hsv<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->d_lh, e->d_ls, e->d_lv, e->Ppad,
+                                                                       e->P, e->N, d_out);
+    e->launches++;
+    CK(cudaMemcpyAsync(scenes, d_out, (size_t)n * 3, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d_out);
+    return NVB_OK;
+}
+
+extern "C" int nvb_library_set_shard(nvb_engine *e, int64_t view_offset, int64_t n_total)
+{
+    if (e->N <= 0) return fail(NVB_E_INVALID, "no library");
+    if (view_offset < 0 || view_offset + e->N > n_total) return fail(NVB_E_INVALID, "bad shard");
+    if (n_total >= (1ll << 28) && e->cw != 0.0) return fail(NVB_E_INVALID, "library too large");
+    e->view_offset = view_offset;
+    e->n_total = n_total;
+    return NVB_OK;
+}
+
+// upload G query scenes [G][H][W][3] into the planar glimpse buffers
+static int upload_queries(nvb_engine *e, const uint8_t *scenes_q, int G)
+{
+    int rc = ensure_glimpse_cap(e, G);
+    if (rc) return rc;
+    uint8_t *d_in = nullptr;
+    const long long n = (long long)G * e->P;
+    CK(cudaMalloc(&d_in, (size_t)n * 3));
+    CK(cudaMemcpyAsync(d_in, scenes_q, (size_t)n * 3, cudaMemcpyHostToDevice, e->stream));
+    k_hsv_to_planar<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(d_in, e->Ppad, e->P, G, e->d_gh,
+                                                                       e->d_gs, e->d_gv);
+    e->launches++;
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d_in);
+    return NVB_OK;
+}
+
+extern "C" int nvb_familiarity(nvb_engine *e, const uint8_t *scenes_q, int G, double *fam)
+{
+    if (e->N <= 0) return fail(NVB_E_INVALID, "no library");
+    if (G <= 0) return NVB_OK;
+    CK(cudaSetDevice(e->device));
+    int rc = upload_queries(e, scenes_q, G);
+    if (rc) return rc;
+    double *d_fam = nullptr;
+    const long long n = (long long)G * e->N;
+    CK(cudaMalloc(&d_fam, sizeof(double) * n));
+    DistArgs da{};
+    da.gv = e->d_gv; da.gh = e->d_gh; da.gs = e->d_gs;
+    da.lv = e->d_lv; da.lh = e->d_lh; da.ls = e->d_ls;
+    da.G = G; da.N = e->N; da.Ppad = e->Ppad; da.cw = e->cw;
+    k_familiarity_exact<<<(unsigned)((n + 127) / 128), 128, 0, e->stream>>>(da, e->P, (double)e->P,
+                                                                           e->d_div255, d_fam);
+    e->launches++;
+    CK(cudaMemcpyAsync(fam, d_fam, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d_fam);
+    return NVB_OK;
+}
+
+extern "C" int nvb_familiarity_min(nvb_engine *e, const uint8_t *scenes_q, int G, double *min_diff,
+                                   int64_t *view_idx)
+{
+    if (e->N <= 0) return fail(NVB_E_INVALID, "no library");
+    if (G <= 0) return NVB_OK;
+    CK(cudaSetDevice(e->device));
+    int rc = upload_queries(e, scenes_q, G);
+    if (rc) return rc;
+    if ((rc = fill_u64(e, e->d_keys, G, KEY_NONE))) return rc;
+    if ((rc = launch_distance(e, G))) return rc;
+    std::vector<unsigned long long> keys(G);
+    CK(cudaMemcpyAsync(keys.data(), e->d_keys, sizeof(unsigned long long) * G, cudaMemcpyDeviceToHost,
+                       e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    const int ib = (e->cw == 0.0) ? 32 : 28;
+    for (int g = 0; g < G; g++) {
+        const unsigned long long score = keys[g] >> ib;
+        if (min_diff) min_diff[g] = (e->cw == 0.0) ? (double)score : (double)score / 4096.0;
+        if (view_idx) view_idx[g] = (int64_t)(keys[g] & ((1ull << ib) - 1ull));
+    }
+    return NVB_OK;
+}
+
+// ---------------------------------------------------------------------------
+static int ensure_log(nvb_engine *e, int cap, bool want_afam)
+{
+    const bool need_afam = want_afam && (e->log_afam == nullptr || e->log_A != e->A);
+    if (cap <= e->log_cap && !need_afam) return NVB_OK;
+    int new_cap = e->log_cap > 0 ? e->log_cap : 64;
+    while (new_cap < cap) new_cap *= 2;
+    CK(cudaStreamSynchronize(e->stream));
+    const size_t B = e->B;
+    int16_t *nb = nullptr;
+    double *np = nullptr, *ns = nullptr, *na = nullptr;
+    CK(cudaMalloc(&nb, sizeof(int16_t) * B * new_cap));
+    CK(cudaMalloc(&np, sizeof(double) * 3 * B * new_cap));
+    CK(cudaMalloc(&ns, sizeof(double) * B * new_cap));
+    const bool keep_afam = want_afam || e->log_afam != nullptr;
+    if (keep_afam) {
+        CK(cudaMalloc(&na, sizeof(double) * B * e->A * new_cap));
+        CK(cudaMemset(na, 0xFF, sizeof(double) * B * e->A * new_cap));
+    }
+    if (e->steps_done > 0 && e->log_best) {
+        const size_t k = e->steps_done;
+        CK(cudaMemcpy(nb, e->log_best, sizeof(int16_t) * B * k, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(np, e->log_pose, sizeof(double) * 3 * B * k, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(ns, e->log_sfam, sizeof(double) * B * k, cudaMemcpyDeviceToDevice));
+        if (na && e->log_afam && e->log_A == e->A)
+            CK(cudaMemcpy(na, e->log_afam, sizeof(double) * B * e->A * k, cudaMemcpyDeviceToDevice));
+    }
+    free_dev(e->log_best); free_dev(e->log_pose); free_dev(e->log_sfam); free_dev(e->log_afam);
+    e->log_best = nb; e->log_pose = np; e->log_sfam = ns; e->log_afam = na;
+    e->log_cap = new_cap;
+    e->log_A = e->A;
+    return NVB_OK;
+}
+
+extern "C" int nvb_agents_set(nvb_engine *e, const double *poses, const int32_t *budget, int B)
+{
+    if (!e->d_land || !e->have_sensor || e->A <= 0) return fail(NVB_E_INVALID, "world not configured");
+    if (e->N <= 0) return fail(NVB_E_INVALID, "no library");
+    if (B <= 0 || !poses) return fail(NVB_E_INVALID, "bad agents");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    int rc;
+    if (B != e->B) {
+        if ((rc = alloc_dev(&e->ag.poses, (size_t)3 * B))) return rc;
+        if ((rc = alloc_dev(&e->ag.status, (size_t)B))) return rc;
+        if ((rc = alloc_dev(&e->ag.completed, (size_t)B))) return rc;
+        if ((rc = alloc_dev(&e->ag.budget, (size_t)B))) return rc;
+        if ((rc = alloc_dev(&e->ag.nav_frames, (size_t)B))) return rc;
+        if ((rc = alloc_dev(&e->ag.err_sum, (size_t)B))) return rc;
+        if ((rc = alloc_dev(&e->ag.err_n, (size_t)B))) return rc;
+        if ((rc = alloc_dev(&e->ag.stepped, (size_t)B))) return rc;
+        if ((rc = alloc_dev(&e->ag.coverage, (size_t)B * (e->n_path > 0 ? e->n_path : 1)))) return rc;
+        free_dev(e->log_best); free_dev(e->log_pose); free_dev(e->log_sfam); free_dev(e->log_afam);
+        e->log_best = nullptr; e->log_pose = e->log_sfam = e->log_afam = nullptr;
+        e->log_cap = 0;
+        e->B = B;
+    }
+    if ((rc = ensure_glimpse_cap(e, (long long)B * e->A))) return rc;
+    CK(cudaMemcpyAsync(e->ag.poses, poses, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, e->stream));
+    if (budget) {
+        CK(cudaMemcpyAsync(e->ag.budget, budget, sizeof(int32_t) * B, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        std::vector<int32_t> big(B, 0x7FFFFFFF);
+        CK(cudaMemcpyAsync(e->ag.budget, big.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    CK(cudaMemsetAsync(e->ag.status, 0, sizeof(int32_t) * B, e->stream));
+    CK(cudaMemsetAsync(e->ag.completed, 0, sizeof(int32_t) * B, e->stream));
+    CK(cudaMemsetAsync(e->ag.nav_frames, 0, sizeof(int32_t) * B, e->stream));
+    CK(cudaMemsetAsync(e->ag.err_sum, 0, sizeof(double) * B, e->stream));
+    CK(cudaMemsetAsync(e->ag.err_n, 0, sizeof(int32_t) * B, e->stream));
+    CK(cudaMemsetAsync(e->ag.stepped, 0, sizeof(int32_t) * B, e->stream));
+    CK(cudaMemsetAsync(e->ag.coverage, 0, (size_t)B * (e->n_path > 0 ? e->n_path : 1), e->stream));
+    CK(cudaMemsetAsync(e->d_step, 0xFF, sizeof(int), e->stream));   // -1: first step bumps it to 0
+    CK(cudaMemsetAsync(e->d_tie_count, 0, sizeof(int), e->stream));
+    e->steps_done = 0;
+    CK(cudaStreamSynchronize(e->stream));
+    return NVB_OK;
+}
+
+static StepArgs make_step_args(nvb_engine *e, int fake, int log_afam)
+{
+    StepArgs s;
+    s.ag = e->ag;
+    s.B = e->B; s.A = e->A; s.N = e->N; s.P = e->P; s.Ppad = e->Ppad;
+    s.offsets = e->d_offsets;
+    s.gv = e->d_gv; s.gh = e->d_gh; s.gs = e->d_gs;
+    s.lv = e->d_lv; s.lh = e->d_lh; s.ls = e->d_ls;
+    s.path = e->d_path; s.n_path = e->n_path;
+    s.view_offset = e->view_offset;
+    s.keys = e->d_keys; s.exact = e->d_exact;
+    s.idx_bits = (e->cw == 0.0) ? 32 : 28;
+    s.band = (e->cw == 0.0) ? 0ull : 1ull;
+    s.cw = e->cw;
+    s.div255 = e->d_div255;
+    s.maxfam = (double)e->P;
+    s.step_size = e->step_size; s.max_dist = e->max_dist;
+    s.threshold_factor = e->thf; s.coverage_factor = e->cvf;
+    s.fake = fake;
+    s.tie_count = e->d_tie_count; s.tie_items = e->d_tie_items; s.tie_thr = e->d_tie_thr;
+    s.step_counter = e->d_step;
+    s.log_cap = e->log_cap;
+    s.log_best = e->log_best; s.log_pose = e->log_pose; s.log_sfam = e->log_sfam;
+    s.log_afam = log_afam ? e->log_afam : nullptr;
+    return s;
+}
+
+static int phase1(nvb_engine *e)
+{
+    k3_begin_step<<<1, 32, 0, e->stream>>>(e->d_step, e->d_tie_count);
+    e->launches++;
+    SamplerArgs sa;
+    sa.w = make_world(e);
+    sa.poses = e->ag.poses; sa.offsets = e->d_offsets; sa.cs = nullptr;
+    sa.A = e->A; sa.agent_mode = 1; sa.need_hs = (e->cw != 0.0);
+    sa.status = e->ag.status; sa.completed = e->ag.completed; sa.budget = e->ag.budget;
+    sa.gv = e->d_gv; sa.gh = e->d_gh; sa.gs = e->d_gs;
+    sa.keys = e->d_keys;
+    int rc = launch_sampler(e, sa, e->B);
+    if (rc) return rc;
+    return launch_distance(e, e->B * e->A);
+}
+
+static int phase2(nvb_engine *e, const StepArgs &s)
+{
+    k3_decide<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
+    k3_ties<<<e->sm_count * 4, NVB_TIE_THREADS, 0, e->stream>>>(s);
+    e->launches += 2;
+    CK(cudaGetLastError());
+    return NVB_OK;
+}
+
+static int phase3(nvb_engine *e, const StepArgs &s)
+{
+    k3_move<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
+    e->launches++;
+    CK(cudaGetLastError());
+    return NVB_OK;
+}
+
+static int check_step_ready(nvb_engine *e, int fake)
+{
+    if (e->B <= 0) return fail(NVB_E_INVALID, "no agents set");
+    if (!fake && e->n_path <= 0) return fail(NVB_E_INVALID, "no training path bound");
+    return NVB_OK;
+}
+
+extern "C" int nvb_agents_step(nvb_engine *e, int nsteps, int fake, int log_afam)
+{
+    int rc = check_step_ready(e, fake);
+    if (rc) return rc;
+    if (nsteps <= 0) return NVB_OK;
+    CK(cudaSetDevice(e->device));
+    if ((rc = ensure_log(e, e->steps_done + nsteps, log_afam != 0))) return rc;
+    const StepArgs s = make_step_args(e, fake, log_afam);
+    for (int i = 0; i < nsteps; i++) {
+        if ((rc = phase1(e))) return rc;
+        if ((rc = phase2(e, s))) return rc;
+        if ((rc = phase3(e, s))) return rc;
+    }
+    e->steps_done += nsteps;
+    return NVB_OK;
+}
+
+extern "C" int nvb_agents_phase(nvb_engine *e, int phase, int fake, int log_afam)
+{
+    int rc = check_step_ready(e, fake);
+    if (rc) return rc;
+    CK(cudaSetDevice(e->device));
+    if (phase == 1) {
+        if ((rc = ensure_log(e, e->steps_done + 1, log_afam != 0))) return rc;
+        return phase1(e);
+    }
+    const StepArgs s = make_step_args(e, fake, log_afam);
+    if (phase == 2) return phase2(e, s);
+    if (phase == 3) {
+        rc = phase3(e, s);
+        if (!rc) e->steps_done += 1;
+        return rc;
+    }
+    return fail(NVB_E_INVALID, "phase must be 1, 2 or 3");
+}
+
+extern "C" int nvb_agents_steps_done(nvb_engine *e) { return e->steps_done; }
+
+extern "C" int nvb_agents_get(nvb_engine *e, double *poses, int32_t *status, int32_t *completed,
+                              int32_t *nav_frames, double *err_sum, int32_t *err_n, uint8_t *coverage)
+{
+    if (e->B <= 0) return fail(NVB_E_INVALID, "no agents set");
+    CK(cudaSetDevice(e->device));
+    const size_t B = e->B;
+    if (poses) CK(cudaMemcpyAsync(poses, e->ag.poses, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, e->stream));
+    if (status) CK(cudaMemcpyAsync(status, e->ag.status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, e->stream));
+    if (completed) CK(cudaMemcpyAsync(completed, e->ag.completed, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, e->stream));
+    if (nav_frames) CK(cudaMemcpyAsync(nav_frames, e->ag.nav_frames, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, e->stream));
+    if (err_sum) CK(cudaMemcpyAsync(err_sum, e->ag.err_sum, sizeof(double) * B, cudaMemcpyDeviceToHost, e->stream));
+    if (err_n) CK(cudaMemcpyAsync(err_n, e->ag.err_n, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, e->stream));
+    if (coverage && e->n_path > 0)
+        CK(cudaMemcpyAsync(coverage, e->ag.coverage, B * e->n_path, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return NVB_OK;
+}
+
+extern "C" int nvb_agents_log(nvb_engine *e, int step0, int nsteps, int16_t *best_idx, double *poses,
+                              double *step_fam, double *afam)
+{
+    if (e->B <= 0) return fail(NVB_E_INVALID, "no agents set");
+    if (step0 < 0 || nsteps < 0 || step0 + nsteps > e->steps_done)
+        return fail(NVB_E_INVALID, "log range [%d, %d) outside the %d logged steps", step0,
+                    step0 + nsteps, e->steps_done);
+    if (afam && !e->log_afam) return fail(NVB_E_INVALID, "angle_familiarity was not logged");
+    CK(cudaSetDevice(e->device));
+    const size_t B = e->B, o = (size_t)step0, k = (size_t)nsteps;
+    if (k == 0) return NVB_OK;
+    if (best_idx)
+        CK(cudaMemcpyAsync(best_idx, e->log_best + o * B, sizeof(int16_t) * B * k, cudaMemcpyDeviceToHost, e->stream));
+    if (poses)
+        CK(cudaMemcpyAsync(poses, e->log_pose + o * B * 3, sizeof(double) * 3 * B * k, cudaMemcpyDeviceToHost, e->stream));
+    if (step_fam)
+        CK(cudaMemcpyAsync(step_fam, e->log_sfam + o * B, sizeof(double) * B * k, cudaMemcpyDeviceToHost, e->stream));
+    if (afam)
+        CK(cudaMemcpyAsync(afam, e->log_afam + o * B * e->A, sizeof(double) * B * e->A * k, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return NVB_OK;
+}
+
+extern "C" void *nvb_device_ptr(nvb_engine *e, int which)
+{
+    switch (which) {
+    case NVB_PTR_KEYS: return e->d_keys;
+    case NVB_PTR_TIE: return e->d_exact;
+    case NVB_PTR_POSES: return e->ag.poses;
+    }
+    return nullptr;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" double nvb_probe_sad_peak(nvb_engine *e, int iters)
+{
+    if (cudaSetDevice(e->device) != cudaSuccess) return -1.0;
+    uint32_t *d_sink = nullptr;
+    if (cudaMalloc(&d_sink, 64) != cudaSuccess) return -1.0;
+    const int grid = e->sm_count * 8, threads = 256;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    k_probe_sad<<<grid, threads, 0, e->stream>>>(iters, 12345u, d_sink);   // warm-up
+    cudaEventRecord(t0, e->stream);
+    k_probe_sad<<<grid, threads, 0, e->stream>>>(iters, 12345u, d_sink);
+    cudaEventRecord(t1, e->stream);
+    e->launches += 2;
+    cudaStreamSynchronize(e->stream);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(d_sink);
+    if (ms <= 0) return -1.0;
+    return (double)grid * threads * (double)iters * 32.0 * 4.0 / (ms * 1e-3);
+}
+
+extern "C" double nvb_time_distance_kernel(nvb_engine *e, int reps)
+{
+    if (e->B <= 0 || e->N <= 0 || reps <= 0) return -1.0;
+    if (cudaSetDevice(e->device) != cudaSuccess) return -1.0;
+    const int G = e->B * e->A;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    fill_u64(e, e->d_keys, G, KEY_NONE);
+    launch_distance(e, G);
+    cudaStreamSynchronize(e->stream);
+    float total = 0;
+    for (int r = 0; r < reps; r++) {
+        fill_u64(e, e->d_keys, G, KEY_NONE);
+        cudaEventRecord(t0, e->stream);
+        launch_distance(e, G);
+        cudaEventRecord(t1, e->stream);
+        cudaStreamSynchronize(e->stream);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t0, t1);
+        total += ms;
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    return total / reps;
+}

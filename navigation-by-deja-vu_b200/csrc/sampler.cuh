@@ -1,0 +1,274 @@
+// sampler.cuh -- K1: glimpse extraction for all agents x headings.
+//
+// Replaces, fused into one launch per step-batch:
+//   fill_sensor_from   navsim/util.pyx:137-168          (nearest-neighbour rotated gather)
+//   downscale_chem     navsim/util.pyx:91-134           (block mean / hue vote / S quirk)
+//   quantise + mask    navsim/NavBySceneFamiliarity.py:175-192
+//   bounds test        navsim/NavBySceneFamiliarity.py:153-158
+//
+// One CTA per agent (or per pose).  The landscape window the rotated sensor can
+// reach is staged in shared memory by TMA (one 3-D tensor-map box per plane);
+// all A headings of the agent gather from it.  Samples that leave the window
+// (negative-index wrap-around, util.pyx:165-168 with wraparound on) fall back
+// to global memory.  Output: planar glimpses gv/gh/gs [G][Ppad].
+#pragma once
+#include "common.cuh"
+
+struct SamplerArgs {
+    NvbWorld w;
+    const double *poses;     // [B][3] x, y, angle
+    const double *offsets;   // [A] heading offsets (agent mode) or nullptr
+    const double *cs;        // [B][2] host cos/sin of -(pi/2 - angle) (pose mode) or nullptr
+    int A;
+    int agent_mode;          // 1: resident stepping loop, 0: explicit pose list (A == 1)
+    int need_hs;             // also produce the H and S planes
+    int32_t *status;         // agent mode: agent status (in/out); pose mode: [B] out
+    const int32_t *completed;  // agent mode: frames completed
+    const int32_t *budget;     // agent mode: frame budget
+    uint8_t *gv, *gh, *gs;   // [B*A][Ppad]
+    unsigned long long *keys;  // [B*A] reset to ~0 (agent mode) or nullptr
+};
+
+#define NVB_SAMPLER_THREADS 256
+
+// Host + device: dynamic shared memory of k1_sample.
+__host__ __device__ inline size_t nvb_sampler_smem(int BW, int BH, int nplanes, int A)
+{
+    size_t win = (size_t)nvb_round_up(BW * BH, 128) * (size_t)nplanes;
+    return win + (size_t)A * 16 + 64;
+}
+
+__global__ void __launch_bounds__(NVB_SAMPLER_THREADS)
+k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem_k1[];
+    uint8_t *smem = smem_k1;
+    const NvbWorld &w = a.w;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int nplanes = a.need_hs ? 3 : 1;
+    const int use_win = (w.R > 0);
+    const size_t plane_sz = use_win ? (size_t)nvb_round_up(w.BW * w.BH, 128) : 0;
+    uint8_t *win_v = smem;                       // plane order in smem: V, H, S
+    uint8_t *win_h = smem + plane_sz;
+    uint8_t *win_s = smem + 2 * plane_sz;
+    double *cs_sm = (double *)(smem + plane_sz * nplanes);
+    uint64_t *mbar = (uint64_t *)(cs_sm + 2 * a.A);
+
+    __shared__ int s_go;
+    __shared__ int s_err;
+
+    const double x = a.poses[3 * b], y = a.poses[3 * b + 1], ang = a.poses[3 * b + 2];
+
+    if (tid == 0) {
+        int go = 1;
+        if (a.agent_mode) {
+            go = (a.status[b] == 0) && (a.completed[b] < a.budget[b]);
+        }
+        if (go) {
+            // NavBySceneFamiliarity.py:156-158
+            if (x <= w.r || y <= w.r || x >= (double)w.cols - w.r || y >= (double)w.rows - w.r) {
+                a.status[b] = -2;
+                go = 0;
+            } else if (!a.agent_mode) {
+                a.status[b] = 0;
+            }
+        }
+        s_go = go;
+        s_err = 0;
+    }
+    if (a.keys != nullptr)
+        for (int k = tid; k < a.A; k += blockDim.x) a.keys[(size_t)b * a.A + k] = NVB_KEY_NONE;
+    __syncthreads();
+    if (!s_go) return;
+
+    const int ox = (int)floor(x) - w.R, oy = (int)floor(y) - w.R;
+    if (use_win && tid == 0) {
+        nvb_mbar_init(mbar, 1);
+        nvb_fence_barrier_init();
+        nvb_mbar_expect_tx(mbar, (uint32_t)(w.BW * w.BH * nplanes));
+        nvb_tma_load_3d(win_v, &tmap, ox, oy, 2, mbar);
+        if (a.need_hs) {
+            nvb_tma_load_3d(win_h, &tmap, ox, oy, 0, mbar);
+            nvb_tma_load_3d(win_s, &tmap, ox, oy, 1, mbar);
+        }
+    }
+    // per-heading rotation, util.pyx:143-145
+    for (int k = tid; k < a.A; k += blockDim.x) {
+        double c, s;
+        if (a.cs != nullptr) {
+            c = a.cs[2 * b];
+            s = a.cs[2 * b + 1];
+        } else {
+            double angle = ang;
+            if (a.agent_mode) angle = nvb_pymod_pos(__dadd_rn(ang, a.offsets[k]), NVB_TWO_PI);
+            double rot = -__dsub_rn(0.5 * NVB_PI, angle);
+            sincos(rot, &s, &c);
+        }
+        cs_sm[2 * k] = c;
+        cs_sm[2 * k + 1] = s;
+    }
+    __syncthreads();
+    if (use_win) nvb_mbar_wait(mbar, 0);
+
+    const double half_w = 0.5 * (double)w.Wpx, half_h = 0.5 * (double)w.Hpx;
+    const uint8_t *land_h = w.land, *land_s = w.land + w.plane_stride,
+                  *land_v = w.land + 2 * w.plane_stride;
+    const int nblk = w.pw * w.ph;
+    const double inv_n = (double)nblk;
+    int err = 0;
+
+    for (int it = tid; it < a.A * w.P; it += blockDim.x) {
+        const int k = it / w.P, p = it - k * w.P;
+        const int bi = p / w.W, bj = p - bi * w.W;
+        const double c = cs_sm[2 * k], s = cs_sm[2 * k + 1];
+        int sum_v = 0;
+        uint8_t hh[NVB_MAX_BLOCK_PX], ss[NVB_MAX_BLOCK_PX];
+        int n = 0;
+        for (int i = 0; i < w.ph; i++) {
+            const double py = (double)(bi * w.ph + i) - half_h;   // util.pyx:160
+            const double pys = __dmul_rn(py, s), pyc = __dmul_rn(py, c);
+            for (int j = 0; j < w.pw; j++) {
+                const double px = (double)(bj * w.pw + j) - half_w;   // util.pyx:159
+                const double rx = __dsub_rn(__dmul_rn(px, c), pys);   // :161
+                const double ry = __dadd_rn(__dmul_rn(px, s), pyc);   // :162
+                long long iy = (long long)round(__dadd_rn(ry, y));    // :166
+                long long ix = (long long)round(__dadd_rn(rx, x));    // :167
+                if (iy < 0) iy += w.rows;
+                if (ix < 0) ix += w.cols;
+                if (iy < 0 || iy >= w.rows || ix < 0 || ix >= w.cols) {
+                    err = 1;
+                    continue;
+                }
+                const int lx = (int)ix - ox, ly = (int)iy - oy;
+                if (use_win && lx >= 0 && lx < w.BW && ly >= 0 && ly < w.BH) {
+                    const int o = ly * w.BW + lx;
+                    sum_v += win_v[o];
+                    if (a.need_hs) { hh[n] = win_h[o]; ss[n] = win_s[o]; }
+                } else {
+                    const size_t o = (size_t)iy * w.pitch + (size_t)ix;
+                    sum_v += __ldg(land_v + o);
+                    if (a.need_hs) { hh[n] = __ldg(land_h + o); ss[n] = __ldg(land_s + o); }
+                }
+                n++;
+            }
+        }
+        // util.pyx:121-123: V = (uint8) round(sum / (fr*fc))
+        uint8_t v = (uint8_t)(int)round(__ddiv_rn((double)sum_v, inv_n));
+        const bool masked = (bj >= w.mask_lo && bj < w.mask_hi);   // NavBySceneFamiliarity.py:189-190
+        const size_t o = ((size_t)b * a.A + k) * w.Ppad + p;
+        a.gv[o] = masked ? 0 : w.lut[512 + v];
+        if (a.need_hs) {
+            // util.pyx:126-132: hue with the largest summed S (strict >, so the
+            // lowest hue wins ties and hue 0 wins when every sum is 0);
+            // S = (uint8) round((conc / fr) * fc) with C integer division.
+            int best_sum = 0, best_h = 0;
+            for (int q = 0; q < n; q++)
+                if (hh[q] == 0) best_sum += ss[q];
+            for (int q = 0; q < n; q++) {
+                int sq = 0;
+                for (int t = 0; t < n; t++)
+                    if (hh[t] == hh[q]) sq += ss[t];
+                if (sq > best_sum || (sq == best_sum && (int)hh[q] < best_h)) {
+                    best_sum = sq;
+                    best_h = hh[q];
+                }
+            }
+            const uint8_t sat = (uint8_t)((best_sum / w.ph) * w.pw);
+            a.gh[o] = masked ? 0 : w.lut[best_h];
+            a.gs[o] = masked ? 0 : w.lut[256 + sat];
+        }
+    }
+    if (err) s_err = 1;
+    __syncthreads();
+    if (tid == 0 && s_err) a.status[b] = -3;   // IndexError, util.pyx:165-168
+}
+
+// planar [G][Ppad] x3 -> interleaved [G][P][3] (familiar_scenes / get_sensor_mat layout)
+__global__ void k_planar_to_hsv(const uint8_t *gh, const uint8_t *gs, const uint8_t *gv, int Ppad,
+                                int P, long long G, uint8_t *out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * P) return;
+    long long g = i / P;
+    int p = (int)(i - g * P);
+    size_t o = (size_t)g * Ppad + p;
+    out[3 * i] = gh[o];
+    out[3 * i + 1] = gs[o];
+    out[3 * i + 2] = gv[o];
+}
+
+// interleaved [G][P][3] -> planar [G][Ppad] x3 (pad bytes are zeroed by the caller)
+__global__ void k_hsv_to_planar(const uint8_t *in, int Ppad, int P, long long G, uint8_t *gh,
+                                uint8_t *gs, uint8_t *gv)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * P) return;
+    long long g = i / P;
+    int p = (int)(i - g * P);
+    size_t o = (size_t)g * Ppad + p;
+    gh[o] = in[3 * i];
+    gs[o] = in[3 * i + 1];
+    gv[o] = in[3 * i + 2];
+}
+
+// Stand-alone A1 (util.pyx:137-168) for the single-call API: one thread per
+// sensor sample, straight from global memory.  cs = host cos/sin.
+__global__ void k_fill_sensor(NvbWorld w, int Hpx, int Wpx, double x, double y, double c, double s,
+                              uint8_t *out, int *err)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Hpx * Wpx) return;
+    int r = i / Wpx, q = i - r * Wpx;
+    double px = (double)q - 0.5 * (double)Wpx, py = (double)r - 0.5 * (double)Hpx;
+    double rx = __dsub_rn(__dmul_rn(px, c), __dmul_rn(py, s));
+    double ry = __dadd_rn(__dmul_rn(px, s), __dmul_rn(py, c));
+    long long iy = (long long)round(__dadd_rn(ry, y));
+    long long ix = (long long)round(__dadd_rn(rx, x));
+    if (iy < 0) iy += w.rows;
+    if (ix < 0) ix += w.cols;
+    if (iy < 0 || iy >= w.rows || ix < 0 || ix >= w.cols) {
+        *err = 1;
+        return;
+    }
+    size_t o = (size_t)iy * w.pitch + (size_t)ix;
+    out[3 * i] = w.land[o];
+    out[3 * i + 1] = w.land[w.plane_stride + o];
+    out[3 * i + 2] = w.land[2 * w.plane_stride + o];
+}
+
+// Stand-alone A2 (util.pyx:91-134): one thread per output pixel.
+__global__ void k_downscale_chem(const uint8_t *img, int R, int C, int fr, int fc, uint8_t *out)
+{
+    int nrb = R / fr, ncb = C / fc;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrb * ncb) return;
+    int bi = i / ncb, bj = i - bi * ncb;
+    long long sum_v = 0;
+    // hue vote without a 256-bin histogram: for every sample, total S of its hue
+    long long best_sum = 0;
+    int best_h = 0;
+    for (int r = 0; r < fr; r++)
+        for (int c = 0; c < fc; c++) {
+            const uint8_t *p = img + ((size_t)(bi * fr + r) * C + (bj * fc + c)) * 3;
+            sum_v += p[2];
+            if (p[0] == 0) best_sum += p[1];
+        }
+    for (int r = 0; r < fr; r++)
+        for (int c = 0; c < fc; c++) {
+            const uint8_t *p = img + ((size_t)(bi * fr + r) * C + (bj * fc + c)) * 3;
+            long long sq = 0;
+            for (int r2 = 0; r2 < fr; r2++)
+                for (int c2 = 0; c2 < fc; c2++) {
+                    const uint8_t *q = img + ((size_t)(bi * fr + r2) * C + (bj * fc + c2)) * 3;
+                    if (q[0] == p[0]) sq += q[1];
+                }
+            if (sq > best_sum || (sq == best_sum && (int)p[0] < best_h)) {
+                best_sum = sq;
+                best_h = p[0];
+            }
+        }
+    out[3 * i + 2] = (uint8_t)(int)round(__ddiv_rn((double)sum_v, (double)((long long)fr * fc)));
+    out[3 * i] = (uint8_t)best_h;
+    out[3 * i + 1] = (uint8_t)((best_sum / fr) * fc);
+}
