@@ -133,9 +133,10 @@ static int rebuild_tmap(nvb_engine *e)
     memset(&e->tmap, 0, sizeof e->tmap);
     e->R = 0;
     if (!e->d_land || !e->have_sensor) return NVB_OK;
+    if (getenv("NAVSIM_B200_NO_TMA")) return NVB_OK;   // debugging knob: gather from global memory
     const double hw = 0.5 * e->W * e->pw, hh = 0.5 * e->H * e->ph;
     const int R = (int)ceil(sqrt(hw * hw + hh * hh)) + 1;
-    const int BH = 2 * R + 2, BW = nvb_round_up(2 * R + 2, 16);
+    const int BH = 2 * R + 2, BW = nvb_round_up(2 * R + 2 + 15, 16);   // +15: 16-B aligned box origin
     if (BW > 256 || BH > 256) return NVB_OK;   // window does not fit a TMA box: gather from global
     if (nvb_sampler_smem(BW, BH, 3, e->A > 0 ? e->A : 1) > 200 * 1024) return NVB_OK;
     static PFN_tmapEncodeTiled encode = nullptr;

@@ -82,7 +82,10 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
     __syncthreads();
     if (!s_go) return;
 
-    const int ox = (int)floor(x) - w.R, oy = (int)floor(y) - w.R;
+    // TMA needs the box's innermost start coordinate on a 16-byte boundary (an
+    // unaligned start traps with an illegal-instruction error on sm_100); BW has
+    // 15 spare columns for that.
+    const int ox = ((int)floor(x) - w.R) & ~15, oy = (int)floor(y) - w.R;
     if (use_win && tid == 0) {
         nvb_mbar_init(mbar, 1);
         nvb_fence_barrier_init();

@@ -1,9 +1,13 @@
 """Parity of the CUDA path (through the C ABI) against the oracle.
 
-Bit-exact for bytes, indices and integer sums; FP64 familiarity values
-bit-exact as well (the kernels keep the reference's operation order); agent
-positions within 1e-9 px (device sin/cos vs glibc may differ in the last bit,
-DESIGN.md "trig parity").
+Bit-exact for bytes, indices and integer sums.  FP64 familiarity values: the
+single-call closure (sads_familiarity) is bit-exact; in the stepping loop
+angle_familiarity is bit-exact unless several views tie at a heading's integer
+minimum, where the reference's max over doubles picks one by rounding noise
+(bound: FAM_RTOL; > 90 % of the values are checked to be bit-exact).  Headings
+that tie for the step's best integer minimum are always resolved in exact FP64
+over every tied view, so the chosen heading index is exact.  Agent positions within POS_TOL (device sin/cos vs
+glibc may differ in the last bit, DESIGN.md "trig parity").
 """
 import numpy as np
 import pytest
@@ -13,6 +17,7 @@ from cases import CASES, agent_grid, build_case
 pytestmark = pytest.mark.gpu
 
 POS_TOL = 1e-9   # px, absolute
+FAM_RTOL = 1e-12  # relative, angle_familiarity of non-winning headings (north_star asks for FP32-level 1e-6)
 
 
 @pytest.fixture(scope="module")
@@ -184,7 +189,7 @@ def test_trajectories_match_oracle(mods, name):
     eng.step(frames, log_afam=True)
     log = eng.log(0, frames, afam=True)
     st = eng.state()
-    n_tied_steps = 0
+    n_tied_steps = n_exact = n_vals = 0
     for b, p in enumerate(poses):
         ag = ow.new_agent(*p)
         r = ow.run(ag, frames, log_afam=True)
@@ -193,7 +198,10 @@ def test_trajectories_match_oracle(mods, name):
         assert st["completed"][b] == r["completed"]
         assert np.array_equal(log["best_idx"][:n, b], r["best_idx"][:n]), (name, b)
         assert np.all(log["best_idx"][n:, b] == -1)
-        assert np.array_equal(log["afam"][:n, b], r["afam"][:n]), (name, b)
+        assert np.allclose(log["afam"][:n, b], r["afam"][:n], rtol=FAM_RTOL, atol=0), (name, b)
+        assert np.allclose(log["step_fam"][:n, b], r["afam"][:n].max(axis=1), rtol=FAM_RTOL, atol=0), (name, b)
+        n_exact += int(np.sum(log["afam"][:n, b] == r["afam"][:n]))
+        n_vals += n * r["afam"].shape[1]
         assert np.allclose(log["poses"][:n, b], r["pos"][:n], rtol=0, atol=POS_TOL)
         assert st["nav_frames"][b] == ag.navigated_for_frames
         assert st["err_n"][b] == ag.n_nav_err
@@ -203,6 +211,7 @@ def test_trajectories_match_oracle(mods, name):
         n_tied_steps += int(np.sum(np.sum(r["afam"][:n] >= top - 1e-9, axis=1) > 1))
     if name in ("ties", "chem1"):
         assert n_tied_steps > 0       # the tie resolver really was exercised
+    assert n_exact > 0.9 * n_vals      # the overwhelming majority is bit-exact
 
 
 def test_out_of_bounds_and_budget(mods):
@@ -248,8 +257,8 @@ def test_dropin_class_matches_oracle(mods, name):
     try:
         for f in range(frames):
             nsf.step_forward()
-            assert np.array_equal(nsf.angle_familiarity, r["afam"][f])
-            assert nsf.step_familiarity == r["afam"][f].max()
+            assert np.allclose(nsf.angle_familiarity, r["afam"][f], rtol=FAM_RTOL, atol=0)
+            assert np.isclose(nsf.step_familiarity, r["afam"][f].max(), rtol=FAM_RTOL, atol=0)
             done += 1
     except navsim.StopNavigationException as e:
         status = e.get_code()
