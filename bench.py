@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the scene-familiarity hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8 "C2"): 1024 agents on one
+2000x2000 synthetic landscape sharing one library of ~1414 training views;
+sensor 40x2 sensor pixels of 2x4 landscape pixels (P = 80), 10 headings over
+180 degrees, 5 V levels, step 10 px.  One bench "step" is one step-batch: every
+agent sweeps its 10 headings (glimpse sampling), each glimpse is scored against
+the whole library (distance kernel, fused min/argmin), the agent turns to the
+most familiar heading and moves (stepping kernels).
+
+metric  = glimpse x training-view comparisons per second
+          (agents x headings x views x steps / time); agent-steps/s is reported
+          beside it (comparisons/s / (headings x views)).
+value   = device-resident loop, inputs in HBM, CUDA events, L2 flushed between
+          timed steps (cold-L2 steps); value_l2_warm = the same K steps back to back.
+e2e     = per step: pinned host poses -> device, one step-batch, results
+          (heading index, new pose, step familiarity) -> host, one sync.
+N > 1   = weak scaling: every rank runs its own 1024 agents (independent
+          experiments shard trivially; no data-path collective).
+--impl reference = the reference's own CPU implementation (oracle/_ref, compiled
+          from /root/reference by oracle/build_ref.py) on all host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "navigation-by-deja-vu_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+METRIC = "glimpse_x_view_comparisons_per_sec"
+UNIT = "comparisons/s"
+
+WORKLOAD = dict(
+    name="C2: 1024 agents x 10 headings x ~1414 views, sensor 40x2@2x4 (P=80), landscape 2000^2",
+    side=2000, seed=2001, sigma=6.0, sensor=(40, 2, 2, 4), n_test_angles=10, n_sensor_levels=5,
+    step_size=10.0, curve=0.0, agents=1024, max_distance=450.0, rewind_every=100)
+
+
+def build_world_inputs(wl):
+    from navsim import synthetic
+    L = synthetic.make_landscape(wl["seed"], wl["side"], "stitch", sigma=wl["sigma"])
+    tpath = synthetic.training_path_for(L.shape, wl["step_size"], wl["n_test_angles"], wl["curve"])
+    s = wl["sensor"]
+    n = int(round(np.sqrt(wl["agents"])))
+    poses = synthetic.start_pose_grid(tpath, s[0] * s[2], n_lat=n, n_deg=wl["agents"] // n)
+    kw = dict(sensor_dimensions=s[:2], sensor_pixel_dimensions=s[2:], step_size=wl["step_size"],
+              n_test_angles=wl["n_test_angles"], n_sensor_levels=wl["n_sensor_levels"],
+              max_distance_to_training_path=wl["max_distance"])
+    return L, tpath, poses, kw
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while the timed regions run."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+            }
+            while not self._halt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.02)
+        except Exception as e:  # NVML missing: report that, do not invent numbers
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from navsim import NavEngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    wl = WORKLOAD
+    K, W = args.steps, max(args.warmup, 3)
+    L, tpath, poses, kw = build_world_inputs(wl)
+    # everything (engine kernels, L2 flush, timing events) runs on ONE non-default stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng = NavEngine(L, device=local, stream=stream.cuda_stream, **kw)
+    rc, bad = eng.train_from_path(tpath)
+    assert rc == 0, (rc, bad)
+    B, A, N = len(poses), wl["n_test_angles"], eng.n_views
+    P = wl["sensor"][0] * wl["sensor"][1]
+    eng.set_agents(poses)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    rewind_every = wl["rewind_every"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def active_agent_steps():
+        st = eng.state(coverage=False)
+        return int(st["nav_frames"].sum())
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- warm-up (also captures the step graph)
+    eng.rewind()
+    eng.step(W)
+    eng.sync()
+
+    # ---- value: K step-batches, device resident, cold L2 per step, CUDA events
+    eng.rewind()
+    barrier()
+    launches0 = eng.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    agent_steps = 0
+    for i in range(K):
+        if i and i % rewind_every == 0:
+            agent_steps += active_agent_steps()
+            eng.rewind()
+        flush.fill_(i & 0xFF)
+        ev[i][0].record(stream)
+        eng.step(1)
+        ev[i][1].record(stream)
+    barrier()
+    agent_steps += active_agent_steps()
+    gpu_launches = eng.launch_count - launches0
+    t_cold = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    t_cold = max_over_ranks(t_cold)
+
+    # ---- the same K steps back to back (L2 warm: the resident loop as it runs in production)
+    eng.rewind()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    done = 0
+    while done < K:
+        n = min(rewind_every, K - done)
+        eng.step(n)
+        done += n
+        if done < K:
+            eng.rewind()
+    e1.record(stream)
+    barrier()
+    t_warm = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+
+    # ---- sustained load for the clock record (>= ~1.5 s of back-to-back steps)
+    t_s = time.perf_counter()
+    sustained_steps = 0
+    e0.record(stream)
+    while time.perf_counter() - t_s < (0.0 if args.quick else 1.5) or sustained_steps == 0:
+        eng.rewind()
+        eng.step(rewind_every)
+        eng.sync()
+        sustained_steps += rewind_every
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t_sustained = e0.elapsed_time(e1) * 1e-3
+
+    # ---- roofline: distance kernel timed with events inside the step sequence
+    eng.rewind()
+    eng.set_options(use_graph=False, kernel_timing=True)
+    done = 0
+    while done < K:
+        n = min(rewind_every, K - done)
+        eng.step(n)
+        done += n
+        if done < K:
+            eng.rewind()
+    k2_ms, k2_n = eng.kernel_time_ms()
+    eng.set_options(use_graph=True, kernel_timing=False)
+    k2_alone_ms = eng.time_distance_kernel(20)
+    sad_peak = eng.probe_sad_peak(8192)           # pixel-compares / s, register resident
+
+    # ---- e2e: per step pinned host poses in, results out, one sync
+    h_in = torch.empty((B, 3), dtype=torch.float64).pin_memory()
+    h_pose = torch.empty((B, 3), dtype=torch.float64).pin_memory()
+    h_best = torch.empty((B,), dtype=torch.int16).pin_memory()
+    h_fam = torch.empty((B,), dtype=torch.float64).pin_memory()
+    h_in.numpy()[:] = poses
+    eng.set_agents(poses)
+    for _ in range(W):
+        eng.step_io(h_in.numpy(), 1, h_best.numpy(), h_pose.numpy(), h_fam.numpy())
+        h_in.copy_(h_pose)
+    eng.set_agents(poses)
+    h_in.numpy()[:] = poses
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(1 if args.quick else K):
+        if i and i % rewind_every == 0:
+            eng.rewind()
+            h_in.numpy()[:] = poses
+        eng.step_io(h_in.numpy(), 1, h_best.numpy(), h_pose.numpy(), h_fam.numpy())
+        h_in.copy_(h_pose)            # the caller feeds the new poses back in, like a host-driven loop
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0) * (K if args.quick else 1)
+    e2e_result_checksum = float(np.nansum(h_fam.numpy()))
+    barrier()
+    clocks = sampler.stop()
+
+    cmp_per_step = B * A * N * world
+    value = cmp_per_step * K / t_cold
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    k2_s = (k2_ms / max(k2_n, 1)) * 1e-3
+    ops = 2.0 * B * A * N * P                    # algorithmic integer ops per launch
+    alg_bytes = N * P + B * A * P + 8 * B * A    # library + glimpses + keys, V plane only (chem_weight 0)
+    roofline = {
+        "kernel": "k2_sad_v (distance, fused min/argmin)",
+        "bound": "int_alu",
+        "achieved": ops / k2_s / 1e12, "peak": 2.0 * sad_peak / 1e12, "unit": "TOP/s",
+        "frac": (ops / k2_s) / (2.0 * sad_peak),
+        "peak_source": "VABSDIFF4.U8.ACC issue-rate probe measured in this run (nvb_probe_sad_peak); "
+                       "not in MEASURED_PEAKS.json",
+        "launch_ms": k2_s * 1e3, "launch_ms_alone": k2_alone_ms, "launches_timed": k2_n,
+        "hbm_achieved_gbs": alg_bytes / k2_s / 1e9, "hbm_peak_gbs": hbm_peak,
+        "hbm_frac": alg_bytes / k2_s / 1e9 / hbm_peak,
+        "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
+        "traffic": None,
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": t_cold / K * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": wl["name"], "agents_per_gpu": B, "headings": A, "views": N,
+                   "sensor_pixels": P, "landscape": "%dx%d" % (wl["side"], wl["side"]),
+                   "chem_weight": 0.0, "parallelism": "agents sharded x%d, no collective" % world,
+                   "l2": "flushed between timed steps (256 MiB write); value_l2_warm is back to back",
+                   "timing": "CUDA events on the launching stream, max over ranks"},
+        "agent_steps_per_sec": B * world * K / t_cold,
+        "agent_steps_executed": agent_steps,
+        "value_l2_warm": cmp_per_step * K / t_warm,
+        "ms_per_step_l2_warm": t_warm / K * 1e3,
+        "sustained": {"value": B * A * N * sustained_steps / t_sustained, "seconds": t_sustained,
+                      "steps": sustained_steps},
+        "px_compares_per_sec": value * P,
+        "e2e": {"value": cmp_per_step * K / t_e2e, "unit": UNIT,
+                "h2d_bytes_per_step": int(h_in.numel() * 8),
+                "d2h_bytes_per_step": int(h_pose.numel() * 8 + h_best.numel() * 2 + h_fam.numel() * 8),
+                "ms_per_step": t_e2e / K * 1e3, "agent_steps_per_sec": B * world * K / t_e2e,
+                "timing": "host perf_counter around K x (pinned H2D poses + step-batch + D2H results + sync)",
+                "result_checksum": e2e_result_checksum},
+        "gpu_launches": int(gpu_launches),
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+
+    if world == 1 and rank == 0 and not args.no_cpu and not args.quick:
+        line["cpu_baseline"] = cpu_baseline(wl, target_seconds=args.cpu_seconds, cores=args.cores)
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- CPU arm
+def _cpu_worker(argv):
+    """One process = a few agents of the workload, stepped one after another
+    (what `mpirun -n cores` over independent trials does, run_experiment.py:327)."""
+    wl, my_poses, warm, steps, use_ref, barrier = argv
+    L, tpath, _, kw = build_world_inputs(wl)
+    agents = []
+    if use_ref:
+        from oracle import ref_loader
+        ref = ref_loader.load_reference()
+        import warnings
+        warnings.filterwarnings("ignore")
+        for p in my_poses:
+            nsf = ref.NavBySceneFamiliarity(L, familiarity_model=ref.util.sads_familiarity(0.0), **kw)
+            nsf.train_from_path(tpath)
+            nsf.position = (p[0], p[1])
+            nsf.angle = p[2]
+            agents.append(nsf)
+
+        def step(i):
+            try:
+                agents[i].step_forward()
+            except ref.StopNavigationException:
+                agents[i].position = (my_poses[i][0], my_poses[i][1])
+                agents[i].angle = my_poses[i][2]
+                agents[i].reset_error()
+    else:
+        from oracle import oracle as O
+        w = O.World(L, **kw)
+        w.train_from_path(tpath)
+        agents = [w.new_agent(*p) for p in my_poses]
+
+        def step(i):
+            rc, _, _, _ = w.step_forward(agents[i])
+            if rc != 0:
+                agents[i] = w.new_agent(*my_poses[i])
+    for _ in range(warm):
+        for i in range(len(agents)):
+            step(i)
+    barrier.wait()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for i in range(len(agents)):
+            step(i)
+    return time.perf_counter() - t0, len(agents) * steps
+
+
+def cpu_run(wl, agents_per_core, warm, steps, cores, prefer_ref=True):
+    import multiprocessing as mp
+    from oracle import ref_loader
+    use_ref = prefer_ref and ref_loader.available()
+    L, tpath, poses, kw = build_world_inputs(wl)
+    ctx = mp.get_context("fork")
+    barrier = ctx.Manager().Barrier(cores)
+    n = agents_per_core * cores
+    sel = poses[np.linspace(0, len(poses) - 1, n).astype(int)]
+    jobs = [(wl, sel[c * agents_per_core:(c + 1) * agents_per_core], warm, steps, use_ref, barrier)
+            for c in range(cores)]
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    t = max(r[0] for r in res)
+    agent_steps = sum(r[1] for r in res)
+    return t, agent_steps, len(tpath), use_ref
+
+
+def cpu_baseline(wl, target_seconds=15.0, cores=None):
+    cores = cores or os.cpu_count() or 1
+    apc = 2
+    # calibrate on 1 agent/core x 4 steps, then size the sample to ~target_seconds of wall clock
+    t, n, N, use_ref = cpu_run(wl, 1, 1, 4, cores)
+    per_agent_step = t / 4
+    steps = int(max(8, min(4000, target_seconds / max(per_agent_step * apc, 1e-6))))
+    t, n, N, use_ref = cpu_run(wl, apc, 2, steps, cores)
+    A = wl["n_test_angles"]
+    return {"value": n * A * N / t, "unit": UNIT, "cores": cores,
+            "kind": "reference" if use_ref else "port",
+            "agent_steps_per_sec": n / t,
+            "sample": "%d agents (%d per core, one process per core) x %d steps of the same workload, "
+                      "%.1f s wall; %s" % (apc * cores, apc, steps, t,
+                                           "oracle/_ref = navsim/util.pyx + NavBySceneFamiliarity.py compiled unmodified"
+                                           if use_ref else "oracle/navsim_oracle.c restatement")}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOAD
+    cores = args.cores or os.cpu_count() or 1
+    K, W = args.steps, max(args.warmup, 1)
+    apc = 1
+    t, n, N, use_ref = cpu_run(wl, apc, W, K, cores)
+    A = wl["n_test_angles"]
+    value = n * A * N / t
+    P = wl["sensor"][0] * wl["sensor"][1]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t / K * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": wl["name"], "agents_per_gpu": wl["agents"], "headings": A, "views": N,
+                   "sensor_pixels": P, "landscape": "%dx%d" % (wl["side"], wl["side"]), "chem_weight": 0.0,
+                   "sample": "each step = one agent-step of %d agents (one per host core) of the same workload" % n_agents(apc, cores)},
+        "agent_steps_per_sec": n / t,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores,
+                         "kind": "reference" if use_ref else "port",
+                         "sample": "%d agents (one process per core) x %d steps" % (apc * cores, K)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def n_agents(apc, cores):
+    return apc * cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cores", type=int, default=None)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: skip the sustained, e2e and cpu legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -145,6 +145,16 @@ int nvb_agents_set(nvb_engine *e, const double *poses, const int32_t *frame_budg
  * returns after the launches are queued.  log_afam != 0 also logs
  * angle_familiarity per step. */
 int nvb_agents_step(nvb_engine *e, int nsteps, int fake, int log_afam);
+/* Restores the start poses, budgets, counters, coverage and step log of the
+ * last nvb_agents_set() from a device-side snapshot (no host traffic). */
+int nvb_agents_rewind(nvb_engine *e);
+/* One call = host poses in (pinned or pageable; NULL keeps the device poses),
+ * nsteps step-batches, the last step's results back on the host, one
+ * synchronisation: the per-call form a host-driven loop uses (the reference's
+ * step_forward() contract, NavBySceneFamiliarity.py:279, for B agents).
+ * best_idx [B], poses_out [B][3], step_fam [B]; any may be NULL. */
+int nvb_agents_step_io(nvb_engine *e, const double *poses_in, int nsteps, int16_t *best_idx,
+                       double *poses_out, double *step_fam);
 /* Current state (synchronises).  Any pointer may be NULL.  poses [B][3],
  * status [B] (stop codes above), completed [B] (steps that returned normally,
  * scripts/run_experiment.py:243-245), nav_frames [B] (navigated_for_frames),
@@ -173,6 +183,13 @@ int nvb_agents_phase(nvb_engine *e, int phase, int fake, int log_afam);
 #define NVB_PTR_TIE 1  /* uint64 [B*A]  (FP64 bit patterns) */
 #define NVB_PTR_POSES 2 /* double [B][3] */
 void *nvb_device_ptr(nvb_engine *e, int which);
+
+/* use_graph: replay one captured CUDA graph per step-batch (default on).
+ * kernel_timing: record CUDA events around the distance kernel inside the step
+ * sequence (disables graph replay); read back with nvb_kernel_time_ms(), which
+ * returns the summed milliseconds and stores the launch count. */
+int nvb_set_options(nvb_engine *e, int use_graph, int kernel_timing);
+double nvb_kernel_time_ms(nvb_engine *e, int64_t *count);
 
 /* Counters for bench.py: kernels launched by this engine so far. */
 int64_t nvb_launch_count(nvb_engine *e);

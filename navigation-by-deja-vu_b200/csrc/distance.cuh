@@ -28,7 +28,8 @@ struct DistArgs {
     const uint8_t *lv, *lh, *ls;  // library  [N][Ppad]
     int G, N, Ppad;
     int nk;                       // K-chunks per row
-    int n_vt, vt_per_split;       // view tiles, view tiles per blockIdx.y
+    int n_vt, vt_per_split;       // view tiles (and, for the HSV kernel, tiles per blockIdx.y)
+    const int *spans;             // [gridDim.x + 1] unit boundaries per CTA (k2_sad_v)
     long long view_offset;        // global index of local view 0 (library shards)
     unsigned long long *keys;     // [G], pre-set to ~0
     double cw;
@@ -70,10 +71,21 @@ struct DistCfg {
     static constexpr int TN = TX * MV;
     static constexpr int KC = 16 * CPR;
     static constexpr int STAGE_BYTES = (TG + TN) * KC;
-    static constexpr int SMEM = STAGE_BYTES * STAGES;
+    static constexpr int SMEM = STAGE_BYTES * STAGES + 64;   // + mbarriers
 };
 
-template <int TY, int MG, int MV, int CPR, int STAGES>
+// Work decomposition: a "unit" is one TG x TN (glimpse tile x view tile) block,
+// linearised glimpse-tile-major (u = gt * n_vt + vt).  The host cuts the unit list
+// into one contiguous, cost-balanced span per CTA (spans[blockIdx.x] ..
+// spans[blockIdx.x + 1]); a CTA therefore stays on one glimpse tile for nearly its
+// whole span, keeps a per-thread running minimum across its units, and only
+// reduces across lanes / touches global memory when the glimpse tile changes.
+//
+// BULK = true (rows are exactly KC bytes: nk == 1, odd CPR): both operand tiles
+// are contiguous in global memory and are staged by ONE TMA bulk copy each
+// (cp.async.bulk, SASS UBLKCP) completing on a per-stage mbarrier.
+// BULK = false: 16-B cp.async (LDGSTS) with an XOR swizzle, any row length.
+template <int TY, int MG, int MV, int CPR, int STAGES, bool BULK>
 __global__ void __launch_bounds__(NVB_DIST_THREADS, 2)
 k2_sad_v(DistArgs a)
 {
@@ -83,25 +95,45 @@ k2_sad_v(DistArgs a)
     static_assert(MV == 1 || MV == 2 || MV == 4 || MV == 8, "MV must be a power of two <= 8");
     extern __shared__ __align__(1024) uint8_t smem_k2[];
     uint8_t *smem = smem_k2;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGE_BYTES * STAGES);
 
     const int tid = threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;
-    const int g0 = blockIdx.x * TG;
-    const int vt0 = blockIdx.y * a.vt_per_split;
-    const int vt1 = min(vt0 + a.vt_per_split, a.n_vt);
-    const int total = (vt1 - vt0) * a.nk;
+    const int u0 = a.spans[blockIdx.x], u1 = a.spans[blockIdx.x + 1];
+    const int total = (u1 - u0) * a.nk;
     if (total <= 0) return;
 
+    if (BULK) {
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; s++) nvb_mbar_init(full + s, 1);
+            nvb_fence_barrier_init();
+        }
+        __syncthreads();
+    }
+
     auto load_stage = [&](int it) {
-        const int vt = vt0 + it / a.nk, kc = it - (it / a.nk) * a.nk;
+        const int u = u0 + it / a.nk, kc = it - (it / a.nk) * a.nk;
+        const int gt = u / a.n_vt, vt = u - gt * a.n_vt;
         uint8_t *st = smem + (it % STAGES) * C::STAGE_BYTES;
+        if (BULK) {
+            if (tid == 0) {
+                const int rows_g = min(TG, a.G - gt * TG), rows_v = min(TN, a.N - vt * TN);
+                nvb_mbar_expect_tx(full + (it % STAGES), (uint32_t)((rows_g + rows_v) * KC));
+                nvb_bulk_load_1d(st, a.gv + (size_t)gt * TG * KC, (uint32_t)(rows_g * KC),
+                                 full + (it % STAGES));
+                nvb_bulk_load_1d(st + TG * KC, a.lv + (size_t)vt * TN * KC, (uint32_t)(rows_v * KC),
+                                 full + (it % STAGES));
+            }
+            return;
+        }
         const int kbyte = kc * KC;
         for (int q = tid; q < (TG + TN) * CPR; q += NVB_DIST_THREADS) {
             const int row = q / CPR, c = q - row * CPR;
             const uint8_t *src;
             int ok;
             if (row < TG) {
-                const int g = g0 + row;
+                const int g = gt * TG + row;
                 ok = (g < a.G) && (kbyte + 16 * c < a.Ppad);
                 src = a.gv + (size_t)(ok ? g : 0) * a.Ppad + (ok ? kbyte + 16 * c : 0);
             } else {
@@ -120,12 +152,13 @@ k2_sad_v(DistArgs a)
     for (int i = 0; i < MG; i++)
 #pragma unroll
         for (int j = 0; j < MV; j++) acc[i][j] = 0;
+    // running minimum of this thread over the units of the current glimpse tile:
+    // best = (sum << LOGMV) | j, best_vt = view tile it came from
     uint32_t best[MG];
     int best_vt[MG];
 #pragma unroll
     for (int i = 0; i < MG; i++) { best[i] = 0xFFFFFFFFu; best_vt[i] = 0; }
 
-    // per-thread row bases and swizzle terms
     int goff[MG], gsw[MG], voff[MV], vsw[MV];
 #pragma unroll
     for (int i = 0; i < MG; i++) { int r = ty + TY * i; goff[i] = r * KC; gsw[i] = nvb_swz<CPR>(r) << 4; }
@@ -135,14 +168,23 @@ k2_sad_v(DistArgs a)
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
         if (s < total) load_stage(s);
-        nvb_cp_async_commit();
+        if (!BULK) nvb_cp_async_commit();
     }
 
+    constexpr int RW = (TX < 32) ? TX : 32;
+
     for (int it = 0; it < total; it++) {
-        nvb_cp_async_wait<STAGES - 2>();
-        __syncthreads();
+        if (!BULK) nvb_cp_async_wait<STAGES - 2>();
+        __syncthreads();   // everyone is done with job it-1: its slot may be refilled
         if (it + STAGES - 1 < total) load_stage(it + STAGES - 1);
-        nvb_cp_async_commit();
+        if (!BULK) nvb_cp_async_commit();
+        if (BULK) nvb_mbar_wait(full + (it % STAGES), (uint32_t)((it / STAGES) & 1));
+
+        const int u = u0 + it / a.nk, kc = it - (it / a.nk) * a.nk;
+        const int gt = u / a.n_vt, vt = u - gt * a.n_vt;
+        // view groups of this tile that hold at least one real view (edge tile: fewer)
+        const int nvalid = min(TN, a.N - vt * TN);
+        const int jmax = (nvalid + TX - 1) / TX;
 
         const uint8_t *st = smem + (it % STAGES) * C::STAGE_BYTES;
 #pragma unroll(CPR <= 5 ? CPR : 1)
@@ -153,57 +195,61 @@ k2_sad_v(DistArgs a)
                 av[i] = *reinterpret_cast<const uint4 *>(st + goff[i] + ((c << 4) ^ gsw[i]));
 #pragma unroll
             for (int j = 0; j < MV; j++) {
-                const uint4 b = *reinterpret_cast<const uint4 *>(st + voff[j] + ((c << 4) ^ vsw[j]));
+                if (j < jmax) {
+                    const uint4 b = *reinterpret_cast<const uint4 *>(st + voff[j] + ((c << 4) ^ vsw[j]));
 #pragma unroll
-                for (int i = 0; i < MG; i++) {
-                    uint32_t s = acc[i][j];
-                    s = nvb_sad4(av[i].x, b.x, s);
-                    s = nvb_sad4(av[i].y, b.y, s);
-                    s = nvb_sad4(av[i].z, b.z, s);
-                    s = nvb_sad4(av[i].w, b.w, s);
-                    acc[i][j] = s;
+                    for (int i = 0; i < MG; i++) {
+                        uint32_t s = acc[i][j];
+                        s = nvb_sad4(av[i].x, b.x, s);
+                        s = nvb_sad4(av[i].y, b.y, s);
+                        s = nvb_sad4(av[i].z, b.z, s);
+                        s = nvb_sad4(av[i].w, b.w, s);
+                        acc[i][j] = s;
+                    }
                 }
             }
         }
 
-        const int kc = it % a.nk;
         if (kc == a.nk - 1) {
-            const int vt = vt0 + it / a.nk;
-            const bool edge = (vt + 1) * TN > a.N;
+            // unit finished: fold its MG x MV sums into the per-thread running minimum
+            const bool edge = nvalid < TN;
 #pragma unroll
             for (int i = 0; i < MG; i++) {
                 uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
                 for (int j = 0; j < MV; j++) {
-                    uint32_t k = (acc[i][j] << LOGMV) | (uint32_t)j;
-                    if (edge && vt * TN + tx + TX * j >= a.N) k = 0xFFFFFFFFu;
+                    uint32_t k = acc[i][j] * MV + j;
+                    if (edge && tx + TX * j >= nvalid) k = 0xFFFFFFFFu;
                     m = min(m, k);
                     acc[i][j] = 0;
                 }
                 // strict < on the sum alone: an equal sum in a later tile has a higher view index
                 if ((m >> LOGMV) < (best[i] >> LOGMV)) { best[i] = m; best_vt[i] = vt; }
             }
-        }
-    }
-
-    // (sum, view) -> 64-bit keys; min over the TX threads of a glimpse row
-    constexpr int RW = (TX < 32) ? TX : 32;
+            // glimpse tile ends (or span ends): reduce across the TX lanes of each row
+            const bool flush = (it == total - 1) || (vt == a.n_vt - 1);
+            if (flush) {
 #pragma unroll
-    for (int i = 0; i < MG; i++) {
-        unsigned long long key = NVB_KEY_NONE;
-        if (best[i] != 0xFFFFFFFFu) {
-            const unsigned long long sum = best[i] >> LOGMV;
-            const unsigned long long v =
-                (unsigned long long)(a.view_offset + (long long)best_vt[i] * TN + tx + TX * (int)(best[i] & (MV - 1)));
-            key = (sum << a.idx_bits) | v;
-        }
+                for (int i = 0; i < MG; i++) {
+                    unsigned long long key = NVB_KEY_NONE;
+                    if (best[i] != 0xFFFFFFFFu) {
+                        const unsigned long long sum = best[i] >> LOGMV;
+                        const unsigned long long v = (unsigned long long)(
+                            a.view_offset + (long long)best_vt[i] * TN + tx + TX * (int)(best[i] & (MV - 1)));
+                        key = (sum << a.idx_bits) | v;
+                    }
 #pragma unroll
-        for (int o = RW / 2; o > 0; o >>= 1) {
-            unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
-            key = (other < key) ? other : key;
+                    for (int o = RW / 2; o > 0; o >>= 1) {
+                        unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+                        key = (other < key) ? other : key;
+                    }
+                    const int g = gt * TG + ty + TY * i;
+                    if ((tx % RW) == 0 && g < a.G && key != NVB_KEY_NONE) atomicMin(a.keys + g, key);
+                    best[i] = 0xFFFFFFFFu;
+                    best_vt[i] = 0;
+                }
+            }
         }
-        const int g = g0 + ty + TY * i;
-        if ((tx % RW) == 0 && g < a.G && key != NVB_KEY_NONE) atomicMin(a.keys + g, key);
     }
 }
 

@@ -26,7 +26,10 @@ struct SamplerArgs {
     const int32_t *completed;  // agent mode: frames completed
     const int32_t *budget;     // agent mode: frame budget
     uint8_t *gv, *gh, *gs;   // [B*A][Ppad]
-    unsigned long long *keys;  // [B*A] reset to ~0 (agent mode) or nullptr
+    unsigned long long *keys;  // [B*A] reset to "none" (agent mode) or nullptr
+    int *step_counter;       // agent mode: bumped once per step-batch (block 0), else nullptr
+    int *tie_count;          // agent mode: tie work list length, reset per step-batch
+    float band;              // FP32 fast path: distance from a rounding tie below which FP64 decides
 };
 
 #define NVB_SAMPLER_THREADS 256
@@ -79,6 +82,12 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
     }
     if (a.keys != nullptr)
         for (int k = tid; k < a.A; k += blockDim.x) a.keys[(size_t)b * a.A + k] = NVB_KEY_NONE;
+    if (a.step_counter != nullptr && b == 0 && tid == 0) {
+        // start of a step-batch: next log slot, empty tie list (nobody reads either
+        // before this kernel has finished)
+        *a.step_counter += 1;
+        *a.tie_count = 0;
+    }
     __syncthreads();
     if (!s_go) return;
 
@@ -118,25 +127,43 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
     const uint8_t *land_h = w.land, *land_s = w.land + w.plane_stride,
                   *land_v = w.land + 2 * w.plane_stride;
     const int nblk = w.pw * w.ph;
-    const double inv_n = (double)nblk;
+    // FP32 fast path: sample coordinate relative to floor(x), floor(y).  Its error is
+    // far below a.band; only samples that land within a.band of a rounding tie are
+    // re-evaluated with the reference's exact FP64 expression (util.pyx:159-167), so
+    // every index is the one the reference computes.
+    const double fx = floor(x), fy = floor(y);
+    const int xi = (int)fx, yi = (int)fy;
+    const float xf = (float)(x - fx), yf = (float)(y - fy);
     int err = 0;
 
     for (int it = tid; it < a.A * w.P; it += blockDim.x) {
         const int k = it / w.P, p = it - k * w.P;
         const int bi = p / w.W, bj = p - bi * w.W;
         const double c = cs_sm[2 * k], s = cs_sm[2 * k + 1];
+        const float cf = (float)c, sf = (float)s;
         int sum_v = 0;
         uint8_t hh[NVB_MAX_BLOCK_PX], ss[NVB_MAX_BLOCK_PX];
         int n = 0;
         for (int i = 0; i < w.ph; i++) {
-            const double py = (double)(bi * w.ph + i) - half_h;   // util.pyx:160
-            const double pys = __dmul_rn(py, s), pyc = __dmul_rn(py, c);
+            const float pyf = (float)(bi * w.ph + i) - (float)half_h;
             for (int j = 0; j < w.pw; j++) {
-                const double px = (double)(bj * w.pw + j) - half_w;   // util.pyx:159
-                const double rx = __dsub_rn(__dmul_rn(px, c), pys);   // :161
-                const double ry = __dadd_rn(__dmul_rn(px, s), pyc);   // :162
-                long long iy = (long long)round(__dadd_rn(ry, y));    // :166
-                long long ix = (long long)round(__dadd_rn(rx, x));    // :167
+                const float pxf = (float)(bj * w.pw + j) - (float)half_w;
+                const float tx = fmaf(pxf, cf, fmaf(-pyf, sf, xf)) + 0.5f;
+                const float ty = fmaf(pxf, sf, fmaf(pyf, cf, yf)) + 0.5f;
+                const float flx = floorf(tx), fly = floorf(ty);
+                const float dx = tx - flx, dy = ty - fly;
+                long long ix, iy;
+                if (dx < a.band || dx > 1.0f - a.band || dy < a.band || dy > 1.0f - a.band) {
+                    const double px = (double)(bj * w.pw + j) - half_w;   // util.pyx:159
+                    const double py = (double)(bi * w.ph + i) - half_h;   // util.pyx:160
+                    const double rx = __dsub_rn(__dmul_rn(px, c), __dmul_rn(py, s));   // :161
+                    const double ry = __dadd_rn(__dmul_rn(px, s), __dmul_rn(py, c));   // :162
+                    iy = (long long)round(__dadd_rn(ry, y));              // :166
+                    ix = (long long)round(__dadd_rn(rx, x));              // :167
+                } else {
+                    ix = (long long)(xi + (int)flx);
+                    iy = (long long)(yi + (int)fly);
+                }
                 if (iy < 0) iy += w.rows;
                 if (ix < 0) ix += w.cols;
                 if (iy < 0 || iy >= w.rows || ix < 0 || ix >= w.cols) {
@@ -156,8 +183,10 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
                 n++;
             }
         }
-        // util.pyx:121-123: V = (uint8) round(sum / (fr*fc))
-        uint8_t v = (uint8_t)(int)round(__ddiv_rn((double)sum_v, inv_n));
+        // util.pyx:121-123: V = (uint8) round(sum / (fr*fc)), half away from zero.  In
+        // integers: the quotient is either an exact tie or at least 1/(2*fr*fc) away
+        // from one, far more than the FP64 division's rounding.
+        uint8_t v = (uint8_t)((2 * sum_v + nblk) / (2 * nblk));
         const bool masked = (bj >= w.mask_lo && bj < w.mask_hi);   // NavBySceneFamiliarity.py:189-190
         const size_t o = ((size_t)b * a.A + k) * w.Ppad + p;
         a.gv[o] = masked ? 0 : w.lut[512 + v];

@@ -64,15 +64,6 @@ __device__ __forceinline__ bool nvb_agent_active(const AgentState &ag, int b)
     return ag.status[b] == 0 && ag.completed[b] < ag.budget[b];
 }
 
-// bumps the device step counter; first kernel of every step-batch
-__global__ void k3_begin_step(int *step_counter, int *tie_count)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        *step_counter += 1;
-        *tie_count = 0;
-    }
-}
-
 __global__ void __launch_bounds__(NVB_STEP_THREADS)
 k3_decide(StepArgs a)
 {

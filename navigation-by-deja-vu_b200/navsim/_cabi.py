@@ -42,6 +42,10 @@ SIGNATURES = {
     "nvb_familiarity_min": (_i, [_vp, _vp, _i, _vp, _vp]),
     "nvb_agents_set": (_i, [_vp, _vp, _vp, _i]),
     "nvb_agents_step": (_i, [_vp, _i, _i, _i]),
+    "nvb_agents_rewind": (_i, [_vp]),
+    "nvb_agents_step_io": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "nvb_set_options": (_i, [_vp, _i, _i]),
+    "nvb_kernel_time_ms": (_d, [_vp, C.POINTER(_i64)]),
     "nvb_agents_get": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nvb_agents_log": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "nvb_agents_steps_done": (_i, [_vp]),

@@ -37,7 +37,12 @@ class NavEngine(object):
         self._lib = _cabi.lib()
         self._h = C.c_void_p()
         dev = _cabi.default_device() if device is None else int(device)
-        check(self._lib.nvb_engine_create(dev, C.c_void_p(stream) if stream else None,
+        # stream: a cudaStream_t handle (e.g. torch.cuda.Stream().cuda_stream).  None:
+        # the engine makes its own stream.  0 is CUDA's legacy default stream, spelled
+        # cudaStreamLegacy (0x1) for the C ABI, where NULL means "make your own".
+        if stream is not None and int(stream) == 0:
+            stream = 1
+        check(self._lib.nvb_engine_create(dev, C.c_void_p(int(stream)) if stream is not None else None,
                                           C.byref(self._h)))
         self.device = dev
         landscape = np.asarray(landscape)
@@ -218,6 +223,26 @@ class NavEngine(object):
     def step(self, nsteps=1, fake=False, log_afam=False):
         """Queues nsteps step-batches (asynchronous)."""
         check(self._lib.nvb_agents_step(self._h, int(nsteps), int(bool(fake)), int(bool(log_afam))))
+
+    def rewind(self):
+        """Back to the start poses of the last set_agents(), device side only."""
+        check(self._lib.nvb_agents_rewind(self._h))
+
+    def step_io(self, poses_in, nsteps, best_idx, poses_out, step_fam):
+        """Host poses in -> nsteps step-batches -> last step's results out, one
+        synchronisation.  Arrays are caller-owned (pinned torch tensors' numpy views
+        in bench.py); poses_in may be None."""
+        check(self._lib.nvb_agents_step_io(self._h, ptr(poses_in), int(nsteps), ptr(best_idx),
+                                           ptr(poses_out), ptr(step_fam)))
+
+    def set_options(self, use_graph=True, kernel_timing=False):
+        check(self._lib.nvb_set_options(self._h, int(bool(use_graph)), int(bool(kernel_timing))))
+
+    def kernel_time_ms(self):
+        """(summed ms, launches) of the distance kernel since set_options(kernel_timing=True)."""
+        n = C.c_int64(0)
+        ms = float(self._lib.nvb_kernel_time_ms(self._h, C.byref(n)))
+        return ms, int(n.value)
 
     def phase(self, which, fake=False, log_afam=False):
         check(self._lib.nvb_agents_phase(self._h, int(which), int(bool(fake)), int(bool(log_afam))))
