@@ -91,8 +91,7 @@ k2_sad_v(DistArgs a)
 {
     using C = DistCfg<TY, MG, MV, CPR, STAGES>;
     constexpr int TX = C::TX, TG = C::TG, TN = C::TN, KC = C::KC;
-    constexpr int LOGMV = (MV == 1) ? 0 : (MV == 2) ? 1 : (MV == 4) ? 2 : 3;
-    static_assert(MV == 1 || MV == 2 || MV == 4 || MV == 8, "MV must be a power of two <= 8");
+    static_assert(MV == 2 || MV == 4 || MV == 8, "MV must be 2, 4 or 8");
     extern __shared__ __align__(1024) uint8_t smem_k2[];
     uint8_t *smem = smem_k2;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGE_BYTES * STAGES);
@@ -100,7 +99,8 @@ k2_sad_v(DistArgs a)
     const int tid = threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;
     const int u0 = a.spans[blockIdx.x], u1 = a.spans[blockIdx.x + 1];
-    const int total = (u1 - u0) * a.nk;
+    const int nk = BULK ? 1 : a.nk;
+    const int total = (u1 - u0) * nk;
     if (total <= 0) return;
 
     if (BULK) {
@@ -112,38 +112,43 @@ k2_sad_v(DistArgs a)
         __syncthreads();
     }
 
-    auto load_stage = [&](int it) {
-        const int u = u0 + it / a.nk, kc = it - (it / a.nk) * a.nk;
-        const int gt = u / a.n_vt, vt = u - gt * a.n_vt;
-        uint8_t *st = smem + (it % STAGES) * C::STAGE_BYTES;
+    // (gt, vt, kc) of the next job to LOAD, advanced incrementally (no divisions in the loop)
+    int l_gt = u0 / a.n_vt, l_vt = u0 - l_gt * a.n_vt, l_kc = 0, l_it = 0;
+    auto load_next = [&]() {
+        uint8_t *st = smem + (l_it % STAGES) * C::STAGE_BYTES;
         if (BULK) {
             if (tid == 0) {
-                const int rows_g = min(TG, a.G - gt * TG), rows_v = min(TN, a.N - vt * TN);
-                nvb_mbar_expect_tx(full + (it % STAGES), (uint32_t)((rows_g + rows_v) * KC));
-                nvb_bulk_load_1d(st, a.gv + (size_t)gt * TG * KC, (uint32_t)(rows_g * KC),
-                                 full + (it % STAGES));
-                nvb_bulk_load_1d(st + TG * KC, a.lv + (size_t)vt * TN * KC, (uint32_t)(rows_v * KC),
-                                 full + (it % STAGES));
+                const int rows_g = min(TG, a.G - l_gt * TG), rows_v = min(TN, a.N - l_vt * TN);
+                nvb_mbar_expect_tx(full + (l_it % STAGES), (uint32_t)((rows_g + rows_v) * KC));
+                nvb_bulk_load_1d(st, a.gv + (size_t)l_gt * TG * KC, (uint32_t)(rows_g * KC),
+                                 full + (l_it % STAGES));
+                nvb_bulk_load_1d(st + TG * KC, a.lv + (size_t)l_vt * TN * KC, (uint32_t)(rows_v * KC),
+                                 full + (l_it % STAGES));
             }
-            return;
+        } else {
+            const int kbyte = l_kc * KC;
+            for (int q = tid; q < (TG + TN) * CPR; q += NVB_DIST_THREADS) {
+                const int row = q / CPR, c = q - row * CPR;
+                const uint8_t *src;
+                int ok;
+                if (row < TG) {
+                    const int g = l_gt * TG + row;
+                    ok = (g < a.G) && (kbyte + 16 * c < a.Ppad);
+                    src = a.gv + (size_t)(ok ? g : 0) * a.Ppad + (ok ? kbyte + 16 * c : 0);
+                } else {
+                    const int v = l_vt * TN + (row - TG);
+                    ok = (v < a.N) && (kbyte + 16 * c < a.Ppad);
+                    src = a.lv + (size_t)(ok ? v : 0) * a.Ppad + (ok ? kbyte + 16 * c : 0);
+                }
+                const int r = (row < TG) ? row : row - TG;
+                uint8_t *dst = st + (row < TG ? 0 : TG * KC) + r * KC + 16 * (c ^ nvb_swz<CPR>(r));
+                nvb_cp_async16(dst, src, ok ? 16 : 0);
+            }
         }
-        const int kbyte = kc * KC;
-        for (int q = tid; q < (TG + TN) * CPR; q += NVB_DIST_THREADS) {
-            const int row = q / CPR, c = q - row * CPR;
-            const uint8_t *src;
-            int ok;
-            if (row < TG) {
-                const int g = gt * TG + row;
-                ok = (g < a.G) && (kbyte + 16 * c < a.Ppad);
-                src = a.gv + (size_t)(ok ? g : 0) * a.Ppad + (ok ? kbyte + 16 * c : 0);
-            } else {
-                const int v = vt * TN + (row - TG);
-                ok = (v < a.N) && (kbyte + 16 * c < a.Ppad);
-                src = a.lv + (size_t)(ok ? v : 0) * a.Ppad + (ok ? kbyte + 16 * c : 0);
-            }
-            const int r = (row < TG) ? row : row - TG;
-            uint8_t *dst = st + (row < TG ? 0 : TG * KC) + r * KC + 16 * (c ^ nvb_swz<CPR>(r));
-            nvb_cp_async16(dst, src, ok ? 16 : 0);
+        l_it++;
+        if (++l_kc == nk) {
+            l_kc = 0;
+            if (++l_vt == a.n_vt) { l_vt = 0; l_gt++; }
         }
     };
 
@@ -152,12 +157,11 @@ k2_sad_v(DistArgs a)
     for (int i = 0; i < MG; i++)
 #pragma unroll
         for (int j = 0; j < MV; j++) acc[i][j] = 0;
-    // running minimum of this thread over the units of the current glimpse tile:
-    // best = (sum << LOGMV) | j, best_vt = view tile it came from
-    uint32_t best[MG];
-    int best_vt[MG];
+    // per-thread running minimum over the units of the current glimpse tile
+    uint32_t best[MG];     // smallest sum so far
+    uint32_t best_at[MG];  // (view tile << 3) | j of the first view that reached it
 #pragma unroll
-    for (int i = 0; i < MG; i++) { best[i] = 0xFFFFFFFFu; best_vt[i] = 0; }
+    for (int i = 0; i < MG; i++) { best[i] = 0xFFFFFFFFu; best_at[i] = 0; }
 
     int goff[MG], gsw[MG], voff[MV], vsw[MV];
 #pragma unroll
@@ -167,24 +171,19 @@ k2_sad_v(DistArgs a)
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
-        if (s < total) load_stage(s);
+        if (s < total) load_next();
         if (!BULK) nvb_cp_async_commit();
     }
 
     constexpr int RW = (TX < 32) ? TX : 32;
+    int gt = u0 / a.n_vt, vt = u0 - gt * a.n_vt, kc = 0;   // job being computed
 
     for (int it = 0; it < total; it++) {
         if (!BULK) nvb_cp_async_wait<STAGES - 2>();
         __syncthreads();   // everyone is done with job it-1: its slot may be refilled
-        if (it + STAGES - 1 < total) load_stage(it + STAGES - 1);
+        if (l_it < total) load_next();
         if (!BULK) nvb_cp_async_commit();
         if (BULK) nvb_mbar_wait(full + (it % STAGES), (uint32_t)((it / STAGES) & 1));
-
-        const int u = u0 + it / a.nk, kc = it - (it / a.nk) * a.nk;
-        const int gt = u / a.n_vt, vt = u - gt * a.n_vt;
-        // view groups of this tile that hold at least one real view (edge tile: fewer)
-        const int nvalid = min(TN, a.N - vt * TN);
-        const int jmax = (nvalid + TX - 1) / TX;
 
         const uint8_t *st = smem + (it % STAGES) * C::STAGE_BYTES;
 #pragma unroll(CPR <= 5 ? CPR : 1)
@@ -195,48 +194,65 @@ k2_sad_v(DistArgs a)
                 av[i] = *reinterpret_cast<const uint4 *>(st + goff[i] + ((c << 4) ^ gsw[i]));
 #pragma unroll
             for (int j = 0; j < MV; j++) {
-                if (j < jmax) {
-                    const uint4 b = *reinterpret_cast<const uint4 *>(st + voff[j] + ((c << 4) ^ vsw[j]));
+                const uint4 b = *reinterpret_cast<const uint4 *>(st + voff[j] + ((c << 4) ^ vsw[j]));
 #pragma unroll
-                    for (int i = 0; i < MG; i++) {
-                        uint32_t s = acc[i][j];
-                        s = nvb_sad4(av[i].x, b.x, s);
-                        s = nvb_sad4(av[i].y, b.y, s);
-                        s = nvb_sad4(av[i].z, b.z, s);
-                        s = nvb_sad4(av[i].w, b.w, s);
-                        acc[i][j] = s;
-                    }
+                for (int i = 0; i < MG; i++) {
+                    uint32_t s = acc[i][j];
+                    s = nvb_sad4(av[i].x, b.x, s);
+                    s = nvb_sad4(av[i].y, b.y, s);
+                    s = nvb_sad4(av[i].z, b.z, s);
+                    s = nvb_sad4(av[i].w, b.w, s);
+                    acc[i][j] = s;
                 }
             }
         }
 
-        if (kc == a.nk - 1) {
-            // unit finished: fold its MG x MV sums into the per-thread running minimum
-            const bool edge = nvalid < TN;
+        if (++kc == nk) {
+            kc = 0;
+            // unit finished: fold its MG x MV sums into the per-thread running minimum.
+            // Views past the end of the library (last tile) are excluded first.
+            const int nvalid = a.N - vt * TN;
+            if (nvalid < TN) {
+#pragma unroll
+                for (int j = 0; j < MV; j++)
+                    if (tx + TX * j >= nvalid) {
+#pragma unroll
+                        for (int i = 0; i < MG; i++) acc[i][j] = 0xFFFFFFFFu;
+                    }
+            }
 #pragma unroll
             for (int i = 0; i < MG; i++) {
-                uint32_t m = 0xFFFFFFFFu;
+                uint32_t m;
+                if (MV == 8)
+                    m = __vimin3_u32(__vimin3_u32(acc[i][0], acc[i][1], acc[i][2]),
+                                     __vimin3_u32(acc[i][3], acc[i][4], acc[i][5]),
+                                     min(acc[i][6], acc[i][7]));
+                else if (MV == 4)
+                    m = min(__vimin3_u32(acc[i][0], acc[i][1], acc[i][2]), acc[i][3]);
+                else
+                    m = min(acc[i][0], acc[i][1]);
+                // strict <: an equal sum in a later tile has a higher view index.  Improving
+                // is rare after the first tiles, so the index search stays off the hot path.
+                if (m < best[i]) {
+                    int jj = MV - 1;
 #pragma unroll
-                for (int j = 0; j < MV; j++) {
-                    uint32_t k = acc[i][j] * MV + j;
-                    if (edge && tx + TX * j >= nvalid) k = 0xFFFFFFFFu;
-                    m = min(m, k);
-                    acc[i][j] = 0;
+                    for (int j = MV - 2; j >= 0; j--)
+                        if (acc[i][j] == m) jj = j;
+                    best[i] = m;
+                    best_at[i] = ((uint32_t)vt << 3) | (uint32_t)jj;
                 }
-                // strict < on the sum alone: an equal sum in a later tile has a higher view index
-                if ((m >> LOGMV) < (best[i] >> LOGMV)) { best[i] = m; best_vt[i] = vt; }
+#pragma unroll
+                for (int j = 0; j < MV; j++) acc[i][j] = 0;
             }
             // glimpse tile ends (or span ends): reduce across the TX lanes of each row
-            const bool flush = (it == total - 1) || (vt == a.n_vt - 1);
-            if (flush) {
+            if (it == total - 1 || vt == a.n_vt - 1) {
 #pragma unroll
                 for (int i = 0; i < MG; i++) {
                     unsigned long long key = NVB_KEY_NONE;
                     if (best[i] != 0xFFFFFFFFu) {
-                        const unsigned long long sum = best[i] >> LOGMV;
                         const unsigned long long v = (unsigned long long)(
-                            a.view_offset + (long long)best_vt[i] * TN + tx + TX * (int)(best[i] & (MV - 1)));
-                        key = (sum << a.idx_bits) | v;
+                            a.view_offset + (long long)(best_at[i] >> 3) * TN + tx + TX * (int)(best_at[i] & 7u));
+                        key = ((unsigned long long)best[i] << a.idx_bits) | v;
                     }
 #pragma unroll
                     for (int o = RW / 2; o > 0; o >>= 1) {
@@ -246,9 +262,10 @@ k2_sad_v(DistArgs a)
                     const int g = gt * TG + ty + TY * i;
                     if ((tx % RW) == 0 && g < a.G && key != NVB_KEY_NONE) atomicMin(a.keys + g, key);
                     best[i] = 0xFFFFFFFFu;
-                    best_vt[i] = 0;
+                    best_at[i] = 0;
                 }
             }
+            if (++vt == a.n_vt) { vt = 0; gt++; }
         }
     }
 }

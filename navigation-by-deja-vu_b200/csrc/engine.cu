@@ -429,8 +429,7 @@ static int launch_dist_cfg2(nvb_engine *e, DistArgs da)
     const long long units = (long long)n_gt * n_vt;
     long long n_cta = (long long)e->sm_count * occ;
     if (n_cta > units) n_cta = units;
-    const int last = da.N - (n_vt - 1) * C::TN;
-    const double edge_cost = (double)((last + C::TX - 1) / C::TX) / MV;
+    const double edge_cost = 1.0;   // every unit computes its full MG x MV tile
     int rc = build_spans(e, n_gt, n_vt, edge_cost, (int)n_cta);
     if (rc) return rc;
     da.n_vt = n_vt;
@@ -973,10 +972,27 @@ static int launch_distance_timed(nvb_engine *e, int G)
     return rc;
 }
 
+// Small un-sharded libraries: decide + ties + move in ONE launch (every agent's CTA
+// scans the library for its own tied headings); otherwise the three-launch form
+// with the grid-wide tie pass.
+#define NVB_FUSED_STEP_MAX_VIEWS 65536
+
+static bool fused_step(const nvb_engine *e)
+{
+    return e->view_offset == 0 && e->n_total == e->N && e->N <= NVB_FUSED_STEP_MAX_VIEWS &&
+           !getenv("NAVSIM_B200_NO_FUSED_STEP");
+}
+
 static int one_step(nvb_engine *e, const StepArgs &s)
 {
     int rc;
     if ((rc = phase1(e))) return rc;
+    if (fused_step(e)) {
+        k3_step<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
+        e->launches++;
+        CK(cudaGetLastError());
+        return NVB_OK;
+    }
     if ((rc = phase2(e, s))) return rc;
     return phase3(e, s);
 }
@@ -1012,7 +1028,6 @@ static int ensure_graph(nvb_engine *e, int fake, int log_afam)
     return NVB_OK;
 }
 
-#define NVB_KERNELS_PER_STEP 5   /* K1, K2, decide, ties, move */
 
 static int run_steps(nvb_engine *e, int nsteps, int fake, int log_afam)
 {
@@ -1028,9 +1043,10 @@ static int run_steps(nvb_engine *e, int nsteps, int fake, int log_afam)
             done = 1;
             if ((rc = ensure_graph(e, fake, log_afam))) return rc;
         }
+        const int per_step = fused_step(e) ? 3 : 5;   // K1, K2, step | K1, K2, decide, ties, move
         for (int i = done; i < nsteps; i++) {
             CK(cudaGraphLaunch(e->graph_exec, e->stream));
-            e->launches += NVB_KERNELS_PER_STEP;
+            e->launches += per_step;
         }
     } else {
         const StepArgs s = make_step_args(e, fake, log_afam);
