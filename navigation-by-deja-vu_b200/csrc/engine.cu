@@ -356,7 +356,10 @@ extern "C" int nvb_set_nav_params(nvb_engine *e, double step_size, double max_di
 // FP32 error of px*c - py*s + frac(x) for |px|, |py| <= half the sensor footprint.
 static float sampler_band(const nvb_engine *e)
 {
-    return 4e-7f * (float)(e->W * e->pw + e->H * e->ph) + 1e-5f;
+    // FP32 error: operand rounding ~6e-8 * footprint, two FMAs and (pw + ph) running adds
+    // of at most half an ulp of the window radius each; the band is > 3x that bound
+    const float foot = (float)(e->W * e->pw + e->H * e->ph);
+    return 4e-7f * foot + 1e-5f + 2e-8f * foot * (float)(e->pw + e->ph);
 }
 
 static int launch_sampler(nvb_engine *e, const SamplerArgs &sa, int nblocks)
@@ -364,12 +367,20 @@ static int launch_sampler(nvb_engine *e, const SamplerArgs &sa, int nblocks)
     const int nplanes = sa.need_hs ? 3 : 1;
     const size_t smem = e->R > 0 ? nvb_sampler_smem(e->BW, e->BH, nplanes, sa.A)
                                  : nvb_sampler_smem(0, 0, 0, sa.A);
-    static size_t attr_set[64] = {0};
-    if (smem > attr_set[e->device & 63]) {
-        CK(cudaFuncSetAttribute(k1_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[e->device & 63] = smem;
+    static size_t attr_set[64][2] = {{0}};
+    size_t &cur = attr_set[e->device & 63][sa.need_hs ? 1 : 0];
+    if (smem > cur || cur == 0) {
+        if (sa.need_hs) {
+            CK(cudaFuncSetAttribute(k1_sample<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        } else {
+            CK(cudaFuncSetAttribute(k1_sample<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        cur = smem;
     }
-    k1_sample<<<nblocks, NVB_SAMPLER_THREADS, smem, e->stream>>>(e->tmap, sa);
+    if (sa.need_hs)
+        k1_sample<true><<<nblocks, NVB_SAMPLER_THREADS, smem, e->stream>>>(e->tmap, sa);
+    else
+        k1_sample<false><<<nblocks, NVB_SAMPLER_THREADS, smem, e->stream>>>(e->tmap, sa);
     e->launches++;
     CK(cudaGetLastError());
     return NVB_OK;

@@ -41,6 +41,46 @@ __host__ __device__ inline size_t nvb_sampler_smem(int BW, int BH, int nplanes, 
     return win + (size_t)A * 16 + 64;
 }
 
+// Sample coordinates (util.pyx:159-168).  The reference evaluates
+//   ix = (ssize_t) round(px*c - py*s + x),  iy = (ssize_t) round(px*s + py*c + y)
+// in FP64.  Here the coordinate relative to (floor x, floor y) is tracked in FP32
+// (one FADD per sample along a sensor-pixel block) and rounded with the
+// add-magic-number trick (no conversion instructions); whenever it lands within
+// `band` of a rounding tie -- band is several times the worst FP32 error -- the
+// reference's exact FP64 expression decides instead.  Every index is therefore
+// exactly the reference's.
+#define NVB_RND_MAGIC 12582912.0f        /* 1.5 * 2^23: (t + M) - M = t rounded to an integer */
+#define NVB_RND_MAGIC_BITS 0x4B400000
+
+struct SampleCtx {
+    double c, s, x, y, half_w, half_h;
+    int xi, yi, rows, cols;
+    float band;
+};
+
+// exact FP64 path + the reference's wrap-around / bounds semantics
+__device__ __noinline__ bool nvb_sample_exact(const SampleCtx &q, int col, int row, int &ix, int &iy)
+{
+    const double px = (double)col - q.half_w;   // util.pyx:159
+    const double py = (double)row - q.half_h;   // util.pyx:160
+    const double rx = __dsub_rn(__dmul_rn(px, q.c), __dmul_rn(py, q.s));   // :161
+    const double ry = __dadd_rn(__dmul_rn(px, q.s), __dmul_rn(py, q.c));   // :162
+    long long ly = (long long)round(__dadd_rn(ry, q.y));                  // :166
+    long long lx = (long long)round(__dadd_rn(rx, q.x));                  // :167
+    // boundscheck on, wraparound on (no decorators at util.pyx:137): a negative
+    // index wraps once; anything still outside raises IndexError
+    if (lx < 0) lx += q.cols;
+    if (ly < 0) ly += q.rows;
+    if (lx < 0 || lx >= q.cols || ly < 0 || ly >= q.rows) return false;
+    ix = (int)lx;
+    iy = (int)ly;
+    return true;
+}
+
+#undef NVB_SAMPLER_THREADS
+#define NVB_SAMPLER_THREADS 128
+
+template <bool NEED_HS>
 __global__ void __launch_bounds__(NVB_SAMPLER_THREADS)
 k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
 {
@@ -49,7 +89,7 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
     const NvbWorld &w = a.w;
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
-    const int nplanes = a.need_hs ? 3 : 1;
+    constexpr int nplanes = NEED_HS ? 3 : 1;
     const int use_win = (w.R > 0);
     const size_t plane_sz = use_win ? (size_t)nvb_round_up(w.BW * w.BH, 128) : 0;
     uint8_t *win_v = smem;                       // plane order in smem: V, H, S
@@ -94,13 +134,15 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
     // TMA needs the box's innermost start coordinate on a 16-byte boundary (an
     // unaligned start traps with an illegal-instruction error on sm_100); BW has
     // 15 spare columns for that.
-    const int ox = ((int)floor(x) - w.R) & ~15, oy = (int)floor(y) - w.R;
+    const double fx = floor(x), fy = floor(y);
+    const int xi = (int)fx, yi = (int)fy;
+    const int ox = (xi - w.R) & ~15, oy = yi - w.R;
     if (use_win && tid == 0) {
         nvb_mbar_init(mbar, 1);
         nvb_fence_barrier_init();
         nvb_mbar_expect_tx(mbar, (uint32_t)(w.BW * w.BH * nplanes));
         nvb_tma_load_3d(win_v, &tmap, ox, oy, 2, mbar);
-        if (a.need_hs) {
+        if (NEED_HS) {
             nvb_tma_load_3d(win_h, &tmap, ox, oy, 0, mbar);
             nvb_tma_load_3d(win_s, &tmap, ox, oy, 1, mbar);
         }
@@ -123,65 +165,83 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
     __syncthreads();
     if (use_win) nvb_mbar_wait(mbar, 0);
 
-    const double half_w = 0.5 * (double)w.Wpx, half_h = 0.5 * (double)w.Hpx;
     const uint8_t *land_h = w.land, *land_s = w.land + w.plane_stride,
                   *land_v = w.land + 2 * w.plane_stride;
     const int nblk = w.pw * w.ph;
-    // FP32 fast path: sample coordinate relative to floor(x), floor(y).  Its error is
-    // far below a.band; only samples that land within a.band of a rounding tie are
-    // re-evaluated with the reference's exact FP64 expression (util.pyx:159-167), so
-    // every index is the one the reference computes.
-    const double fx = floor(x), fy = floor(y);
-    const int xi = (int)fx, yi = (int)fy;
+    SampleCtx q;
+    q.x = x; q.y = y;
+    q.half_w = 0.5 * (double)w.Wpx; q.half_h = 0.5 * (double)w.Hpx;
+    q.xi = xi; q.yi = yi;
+    q.band = a.band;
+    q.rows = w.rows; q.cols = w.cols;
     const float xf = (float)(x - fx), yf = (float)(y - fy);
+    const float tie = 0.5f - a.band;
+    // `safe`: every sample of this agent lies inside the landscape and inside the
+    // staged window (R = reach + 1), so no wrap / bounds / window test is needed
+    const bool safe = use_win && (xi - w.R >= 0) && (xi + w.R + 1 < w.cols) && (yi - w.R >= 0) &&
+                      (yi + w.R + 1 < w.rows);
+    const int wx0 = xi - ox, wy0 = yi - oy;   // window coordinates of (floor x, floor y)
     int err = 0;
 
     for (int it = tid; it < a.A * w.P; it += blockDim.x) {
         const int k = it / w.P, p = it - k * w.P;
         const int bi = p / w.W, bj = p - bi * w.W;
-        const double c = cs_sm[2 * k], s = cs_sm[2 * k + 1];
-        const float cf = (float)c, sf = (float)s;
+        q.c = cs_sm[2 * k]; q.s = cs_sm[2 * k + 1];
+        const float cf = (float)q.c, sf = (float)q.s;
+        const int row0 = bi * w.ph, col0 = bj * w.pw;
+        const float px0 = (float)col0 - (float)q.half_w, py0 = (float)row0 - (float)q.half_h;
+        // coordinate of the block's first sample relative to (floor x, floor y)
+        float tx_row = fmaf(px0, cf, fmaf(-py0, sf, xf));
+        float ty_row = fmaf(px0, sf, fmaf(py0, cf, yf));
         int sum_v = 0;
-        uint8_t hh[NVB_MAX_BLOCK_PX], ss[NVB_MAX_BLOCK_PX];
+        uint8_t hh[NEED_HS ? NVB_MAX_BLOCK_PX : 1], ss[NEED_HS ? NVB_MAX_BLOCK_PX : 1];
         int n = 0;
         for (int i = 0; i < w.ph; i++) {
-            const float pyf = (float)(bi * w.ph + i) - (float)half_h;
+            float tx = tx_row, ty = ty_row;
             for (int j = 0; j < w.pw; j++) {
-                const float pxf = (float)(bj * w.pw + j) - (float)half_w;
-                const float tx = fmaf(pxf, cf, fmaf(-pyf, sf, xf)) + 0.5f;
-                const float ty = fmaf(pxf, sf, fmaf(pyf, cf, yf)) + 0.5f;
-                const float flx = floorf(tx), fly = floorf(ty);
-                const float dx = tx - flx, dy = ty - fly;
-                long long ix, iy;
-                if (dx < a.band || dx > 1.0f - a.band || dy < a.band || dy > 1.0f - a.band) {
-                    const double px = (double)(bj * w.pw + j) - half_w;   // util.pyx:159
-                    const double py = (double)(bi * w.ph + i) - half_h;   // util.pyx:160
-                    const double rx = __dsub_rn(__dmul_rn(px, c), __dmul_rn(py, s));   // :161
-                    const double ry = __dadd_rn(__dmul_rn(px, s), __dmul_rn(py, c));   // :162
-                    iy = (long long)round(__dadd_rn(ry, y));              // :166
-                    ix = (long long)round(__dadd_rn(rx, x));              // :167
+                const float ux = tx + NVB_RND_MAGIC, uy = ty + NVB_RND_MAGIC;
+                const float dx = fabsf(tx - (ux - NVB_RND_MAGIC)), dy = fabsf(ty - (uy - NVB_RND_MAGIC));
+                int lx = __float_as_int(ux) - NVB_RND_MAGIC_BITS, ly = __float_as_int(uy) - NVB_RND_MAGIC_BITS;
+                tx += cf;
+                ty += sf;
+                bool in_win;
+                if (fmaxf(dx, dy) < tie && safe) {
+                    lx += wx0;
+                    ly += wy0;
+                    in_win = true;
                 } else {
-                    ix = (long long)(xi + (int)flx);
-                    iy = (long long)(yi + (int)fly);
+                    int ix, iy;
+                    if (fmaxf(dx, dy) < tie) {
+                        ix = xi + lx;
+                        iy = yi + ly;
+                        if (ix < 0) ix += w.cols;
+                        if (iy < 0) iy += w.rows;
+                        if ((unsigned)ix >= (unsigned)w.cols || (unsigned)iy >= (unsigned)w.rows) {
+                            err = 1;
+                            continue;
+                        }
+                    } else if (!nvb_sample_exact(q, col0 + j, row0 + i, ix, iy)) {
+                        err = 1;
+                        continue;
+                    }
+                    lx = ix - ox;
+                    ly = iy - oy;
+                    in_win = use_win && (unsigned)lx < (unsigned)w.BW && (unsigned)ly < (unsigned)w.BH;
+                    if (!in_win) {
+                        const size_t o = (size_t)iy * w.pitch + (size_t)ix;
+                        sum_v += __ldg(land_v + o);
+                        if (NEED_HS) { hh[n] = __ldg(land_h + o); ss[n] = __ldg(land_s + o); }
+                    }
                 }
-                if (iy < 0) iy += w.rows;
-                if (ix < 0) ix += w.cols;
-                if (iy < 0 || iy >= w.rows || ix < 0 || ix >= w.cols) {
-                    err = 1;
-                    continue;
-                }
-                const int lx = (int)ix - ox, ly = (int)iy - oy;
-                if (use_win && lx >= 0 && lx < w.BW && ly >= 0 && ly < w.BH) {
+                if (in_win) {
                     const int o = ly * w.BW + lx;
                     sum_v += win_v[o];
-                    if (a.need_hs) { hh[n] = win_h[o]; ss[n] = win_s[o]; }
-                } else {
-                    const size_t o = (size_t)iy * w.pitch + (size_t)ix;
-                    sum_v += __ldg(land_v + o);
-                    if (a.need_hs) { hh[n] = __ldg(land_h + o); ss[n] = __ldg(land_s + o); }
+                    if (NEED_HS) { hh[n] = win_h[o]; ss[n] = win_s[o]; }
                 }
                 n++;
             }
+            tx_row -= sf;
+            ty_row += cf;
         }
         // util.pyx:121-123: V = (uint8) round(sum / (fr*fc)), half away from zero.  In
         // integers: the quotient is either an exact tie or at least 1/(2*fr*fc) away
@@ -190,20 +250,20 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
         const bool masked = (bj >= w.mask_lo && bj < w.mask_hi);   // NavBySceneFamiliarity.py:189-190
         const size_t o = ((size_t)b * a.A + k) * w.Ppad + p;
         a.gv[o] = masked ? 0 : w.lut[512 + v];
-        if (a.need_hs) {
+        if (NEED_HS) {
             // util.pyx:126-132: hue with the largest summed S (strict >, so the
             // lowest hue wins ties and hue 0 wins when every sum is 0);
             // S = (uint8) round((conc / fr) * fc) with C integer division.
             int best_sum = 0, best_h = 0;
-            for (int q = 0; q < n; q++)
-                if (hh[q] == 0) best_sum += ss[q];
-            for (int q = 0; q < n; q++) {
+            for (int t = 0; t < n; t++)
+                if (hh[t] == 0) best_sum += ss[t];
+            for (int t = 0; t < n; t++) {
                 int sq = 0;
-                for (int t = 0; t < n; t++)
-                    if (hh[t] == hh[q]) sq += ss[t];
-                if (sq > best_sum || (sq == best_sum && (int)hh[q] < best_h)) {
+                for (int u = 0; u < n; u++)
+                    if (hh[u] == hh[t]) sq += ss[u];
+                if (sq > best_sum || (sq == best_sum && (int)hh[t] < best_h)) {
                     best_sum = sq;
-                    best_h = hh[q];
+                    best_h = hh[t];
                 }
             }
             const uint8_t sat = (uint8_t)((best_sum / w.ph) * w.pw);
