@@ -191,6 +191,10 @@ void *nvb_device_ptr(nvb_engine *e, int which);
 int nvb_set_options(nvb_engine *e, int use_graph, int kernel_timing);
 double nvb_kernel_time_ms(nvb_engine *e, int64_t *count);
 
+/* Tuning aid: one step-batch with per-agent clock64 checkpoints of the fused
+ * step+sample kernel; out [B][8] (SM cycles; 0 = not reached). */
+int nvb_debug_step_clocks(nvb_engine *e, long long *out);
+
 /* Counters for bench.py: kernels launched by this engine so far. */
 int64_t nvb_launch_count(nvb_engine *e);
 /* Integer byte-SIMD issue-rate probe (register-resident VABSDIFF4+accumulate

@@ -30,6 +30,8 @@ struct DistArgs {
     int nk;                       // K-chunks per row
     int n_vt, vt_per_split;       // view tiles (and, for the HSV kernel, tiles per blockIdx.y)
     const int *spans;             // [gridDim.x + 1] unit boundaries per CTA (k2_sad_v)
+    int *step_counter;            // resident loop: device step index, bumped once per launch; else nullptr
+    int *tie_count;               // resident loop: tie work list length, reset per launch
     long long view_offset;        // global index of local view 0 (library shards)
     unsigned long long *keys;     // [G], pre-set to ~0
     double cw;
@@ -86,18 +88,24 @@ struct DistCfg {
 // (cp.async.bulk, SASS UBLKCP) completing on a per-stage mbarrier.
 // BULK = false: 16-B cp.async (LDGSTS) with an XOR swizzle, any row length.
 template <int TY, int MG, int MV, int CPR, int STAGES, bool BULK>
-__global__ void __launch_bounds__(NVB_DIST_THREADS, 2)
+__global__ void __launch_bounds__(NVB_DIST_THREADS, (MG * MV <= 32) ? 3 : 2)
 k2_sad_v(DistArgs a)
 {
     using C = DistCfg<TY, MG, MV, CPR, STAGES>;
     constexpr int TX = C::TX, TG = C::TG, TN = C::TN, KC = C::KC;
-    static_assert(MV == 2 || MV == 4 || MV == 8, "MV must be 2, 4 or 8");
+    static_assert(MV >= 2 && MV <= 16, "MV (views per thread) must be in 2..16");
     extern __shared__ __align__(1024) uint8_t smem_k2[];
     uint8_t *smem = smem_k2;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGE_BYTES * STAGES);
 
     const int tid = threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;
+    if (a.step_counter != nullptr && blockIdx.x == 0 && tid == 0) {
+        // one step-batch = one launch of this kernel: next log slot, empty tie list
+        // (the kernels that read them run after this one)
+        *a.step_counter += 1;
+        *a.tie_count = 0;
+    }
     const int u0 = a.spans[blockIdx.x], u1 = a.spans[blockIdx.x + 1];
     const int nk = BULK ? 1 : a.nk;
     const int total = (u1 - u0) * nk;
@@ -159,9 +167,9 @@ k2_sad_v(DistArgs a)
         for (int j = 0; j < MV; j++) acc[i][j] = 0;
     // per-thread running minimum over the units of the current glimpse tile
     uint32_t best[MG];     // smallest sum so far
-    uint32_t best_at[MG];  // (view tile << 3) | j of the first view that reached it
+    uint32_t best_at[MG];  // (view tile << 4) | j of the first view that reached it
 #pragma unroll
-    for (int i = 0; i < MG; i++) { best[i] = 0xFFFFFFFFu; best_at[i] = 0; }
+    for (int i = 0; i < MG; i++) { best[i] = 0x0FFFFFFFu; best_at[i] = 0; }
 
     int goff[MG], gsw[MG], voff[MV], vsw[MV];
 #pragma unroll
@@ -217,29 +225,23 @@ k2_sad_v(DistArgs a)
                 for (int j = 0; j < MV; j++)
                     if (tx + TX * j >= nvalid) {
 #pragma unroll
-                        for (int i = 0; i < MG; i++) acc[i][j] = 0xFFFFFFFFu;
+                        for (int i = 0; i < MG; i++) acc[i][j] = 0x0FFFFFFFu;   // > any real sum, * 16 fits
                     }
             }
 #pragma unroll
             for (int i = 0; i < MG; i++) {
-                uint32_t m;
-                if (MV == 8)
-                    m = __vimin3_u32(__vimin3_u32(acc[i][0], acc[i][1], acc[i][2]),
-                                     __vimin3_u32(acc[i][3], acc[i][4], acc[i][5]),
-                                     min(acc[i][6], acc[i][7]));
-                else if (MV == 4)
-                    m = min(__vimin3_u32(acc[i][0], acc[i][1], acc[i][2]), acc[i][3]);
-                else
-                    m = min(acc[i][0], acc[i][1]);
-                // strict <: an equal sum in a later tile has a higher view index.  Improving
-                // is rare after the first tiles, so the index search stays off the hot path.
-                if (m < best[i]) {
-                    int jj = MV - 1;
+                // key = sum * 16 + j: the multiply-add runs on the FMA pipe, the 3-input
+                // minimum on the ALU pipe; the smallest key is the smallest sum and, among
+                // equal sums, the lowest view of this thread
+                uint32_t m = acc[i][0] * 16u;
 #pragma unroll
-                    for (int j = MV - 2; j >= 0; j--)
-                        if (acc[i][j] == m) jj = j;
-                    best[i] = m;
-                    best_at[i] = ((uint32_t)vt << 3) | (uint32_t)jj;
+                for (int j = 1; j + 1 < MV; j += 2)
+                    m = __vimin3_u32(m, acc[i][j] * 16u + (uint32_t)j, acc[i][j + 1] * 16u + (uint32_t)(j + 1));
+                if ((MV & 1) == 0) m = min(m, acc[i][MV - 1] * 16u + (uint32_t)(MV - 1));
+                // strict < on the sum alone: an equal sum in a later tile has a higher view index
+                if ((m >> 4) < best[i]) {
+                    best[i] = m >> 4;
+                    best_at[i] = ((uint32_t)vt << 4) | (m & 15u);
                 }
 #pragma unroll
                 for (int j = 0; j < MV; j++) acc[i][j] = 0;
@@ -249,9 +251,9 @@ k2_sad_v(DistArgs a)
 #pragma unroll
                 for (int i = 0; i < MG; i++) {
                     unsigned long long key = NVB_KEY_NONE;
-                    if (best[i] != 0xFFFFFFFFu) {
+                    if (best[i] != 0x0FFFFFFFu) {
                         const unsigned long long v = (unsigned long long)(
-                            a.view_offset + (long long)(best_at[i] >> 3) * TN + tx + TX * (int)(best_at[i] & 7u));
+                            a.view_offset + (long long)(best_at[i] >> 4) * TN + tx + TX * (int)(best_at[i] & 15u));
                         key = ((unsigned long long)best[i] << a.idx_bits) | v;
                     }
 #pragma unroll
@@ -261,7 +263,7 @@ k2_sad_v(DistArgs a)
                     }
                     const int g = gt * TG + ty + TY * i;
                     if ((tx % RW) == 0 && g < a.G && key != NVB_KEY_NONE) atomicMin(a.keys + g, key);
-                    best[i] = 0xFFFFFFFFu;
+                    best[i] = 0x0FFFFFFFu;
                     best_at[i] = 0;
                 }
             }
@@ -303,6 +305,10 @@ k2_sad_hsv(DistArgs a)
     uint8_t *smem = smem_hsv;
     const int g0 = blockIdx.x * NVB_HSV_TG;
     const int tid = threadIdx.x;
+    if (a.step_counter != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+        *a.step_counter += 1;
+        *a.tie_count = 0;
+    }
     const int words = a.Ppad / 4;
     uint32_t *sm = reinterpret_cast<uint32_t *>(smem);
     for (int q = tid; q < 3 * NVB_HSV_TG * words; q += NVB_HSV_THREADS) {

@@ -83,6 +83,7 @@ struct nvb_engine {
     int *d_tie_count = nullptr;
     int2 *d_tie_items = nullptr;
     unsigned long long *d_tie_thr = nullptr;
+    int *d_tie_next = nullptr, *d_tie_ready = nullptr;
     // agents
     int B = 0;
     AgentState ag{};
@@ -90,6 +91,9 @@ struct nvb_engine {
     int steps_done = 0;
     int *d_spans = nullptr;         // per-CTA unit spans of the distance kernel
     int span_key[4] = {-1, -1, -1, -1};
+    long long *d_dbg = nullptr;     // tuning aid: per-agent clock64 checkpoints of one step
+    int32_t *d_pending = nullptr;   // [B] sampler failure parked for the next step (fused loop)
+    bool glimpses_pending = false;  // the glimpses of the next step are already sampled
     double *d_poses0 = nullptr;     // start poses / budgets kept for nvb_agents_rewind
     int32_t *d_budget0 = nullptr;
     // CUDA graph of one step-batch (phase1+2+3), keyed on (fake, log_afam, log buffers)
@@ -192,6 +196,9 @@ static int ensure_glimpse_cap(nvb_engine *e, long long G)
     if ((rc = alloc_dev(&e->d_exact, (size_t)G))) return rc;
     if ((rc = alloc_dev(&e->d_tie_items, (size_t)G))) return rc;
     if ((rc = alloc_dev(&e->d_tie_thr, (size_t)G))) return rc;
+    if ((rc = alloc_dev(&e->d_tie_next, (size_t)G))) return rc;
+    if ((rc = alloc_dev(&e->d_tie_ready, (size_t)G))) return rc;
+    CK(cudaMemsetAsync(e->d_tie_ready, 0, sizeof(int) * (size_t)G, e->stream));
     e->Gcap = G;
     return NVB_OK;
 }
@@ -247,10 +254,10 @@ extern "C" void nvb_engine_destroy(nvb_engine *e)
     cudaStreamSynchronize(e->stream);
     void *ptrs[] = {e->d_land, e->d_lut, e->d_div255, e->d_offsets, e->d_lh, e->d_ls, e->d_lv,
                     e->d_path, e->d_gh, e->d_gs, e->d_gv, e->d_keys, e->d_exact, e->d_tie_count,
-                    e->d_tie_items, e->d_tie_thr, e->ag.poses, e->ag.status, e->ag.completed,
+                    e->d_tie_items, e->d_tie_thr, e->d_tie_next, e->d_tie_ready, e->ag.poses, e->ag.status, e->ag.completed,
                     e->ag.budget, e->ag.nav_frames, e->ag.err_sum, e->ag.err_n, e->ag.coverage,
                     e->ag.stepped, e->d_step, e->log_best, e->log_pose, e->log_sfam, e->log_afam,
-                    e->d_poses0, e->d_budget0, e->d_spans};
+                    e->d_poses0, e->d_budget0, e->d_spans, e->d_pending};
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     for (void *p : ptrs) free_dev(p);
@@ -362,62 +369,56 @@ static float sampler_band(const nvb_engine *e)
     return 4e-7f * foot + 1e-5f + 2e-8f * foot * (float)(e->pw + e->ph);
 }
 
-static int launch_sampler(nvb_engine *e, const SamplerArgs &sa, int nblocks)
+template <bool HS, int PH, int PW>
+static int launch_sampler_t(nvb_engine *e, const SamplerArgs &sa, int nblocks, size_t smem)
 {
-    const int nplanes = sa.need_hs ? 3 : 1;
-    const size_t smem = e->R > 0 ? nvb_sampler_smem(e->BW, e->BH, nplanes, sa.A)
-                                 : nvb_sampler_smem(0, 0, 0, sa.A);
-    static size_t attr_set[64][2] = {{0}};
-    size_t &cur = attr_set[e->device & 63][sa.need_hs ? 1 : 0];
-    if (smem > cur || cur == 0) {
-        if (sa.need_hs) {
-            CK(cudaFuncSetAttribute(k1_sample<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        } else {
-            CK(cudaFuncSetAttribute(k1_sample<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
+    static size_t attr_set[64] = {0};
+    size_t &cur = attr_set[e->device & 63];
+    if (smem > cur) {
+        CK(cudaFuncSetAttribute(k1_sample<HS, PH, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
     }
-    if (sa.need_hs)
-        k1_sample<true><<<nblocks, NVB_SAMPLER_THREADS, smem, e->stream>>>(e->tmap, sa);
-    else
-        k1_sample<false><<<nblocks, NVB_SAMPLER_THREADS, smem, e->stream>>>(e->tmap, sa);
+    k1_sample<HS, PH, PW><<<nblocks, NVB_SAMPLER_THREADS, smem, e->stream>>>(e->tmap, sa);
     e->launches++;
     CK(cudaGetLastError());
     return NVB_OK;
 }
 
-// Cuts the glimpse-tile-major unit list into one contiguous span per CTA with
-// (nearly) equal cost.  A full unit costs 1; the last view tile of every glimpse
-// tile holds fewer views and costs its share of view groups.
-static int build_spans(nvb_engine *e, int n_gt, int n_vt, double edge_cost, int n_cta)
+static int launch_sampler(nvb_engine *e, const SamplerArgs &sa, int nblocks)
+{
+    const int nplanes = sa.need_hs ? 3 : 1;
+    const size_t smem = e->R > 0 ? nvb_sampler_smem(e->BW, e->BH, nplanes, sa.A)
+                                 : nvb_sampler_smem(0, 0, 0, sa.A);
+    if (sa.need_hs) return launch_sampler_t<true, 0, 0>(e, sa, nblocks, smem);
+    // sensor-pixel footprints the reference's drivers use get an unrolled sampling loop
+    if (e->ph == 4 && e->pw == 2) return launch_sampler_t<false, 4, 2>(e, sa, nblocks, smem);
+    if (e->ph == 2 && e->pw == 2) return launch_sampler_t<false, 2, 2>(e, sa, nblocks, smem);
+    if (e->ph == 1 && e->pw == 1) return launch_sampler_t<false, 1, 1>(e, sa, nblocks, smem);
+    return launch_sampler_t<false, 0, 0>(e, sa, nblocks, smem);
+}
+
+// Cuts the glimpse-tile-major unit list into one contiguous span per CTA.  Every
+// unit costs the same, so spans hold floor(units / n_cta) units and the first
+// (units % n_cta) CTAs one more.  CTA b and CTA b + sm_count share an SM
+// (classic launch order), so putting the longer spans first spreads them over
+// distinct SMs instead of stacking two of them on one.
+static int build_spans(nvb_engine *e, int n_gt, int n_vt, int n_cta)
 {
     const long long units = (long long)n_gt * n_vt;
-    if (e->span_key[0] == n_gt && e->span_key[1] == n_vt && e->span_key[2] == n_cta &&
-        e->span_key[3] == (int)(edge_cost * 1024))
-        return NVB_OK;
-    const double over = 0.04;   // per-unit fixed overhead (epilogue, barriers)
-    const double gt_cost = (n_vt - 1) * (1.0 + over) + (edge_cost + over);
-    const double total = gt_cost * n_gt;
+    if (e->span_key[0] == n_gt && e->span_key[1] == n_vt && e->span_key[2] == n_cta) return NVB_OK;
     std::vector<int> spans(n_cta + 1);
-    spans[0] = 0;
+    const long long base = units / n_cta, rem = units % n_cta;
     long long u = 0;
-    double acc = 0.0;
-    for (int c = 1; c <= n_cta; c++) {
-        const double target = total * c / n_cta;
-        while (u < units) {
-            const double cu = ((u % n_vt) == n_vt - 1) ? edge_cost + over : 1.0 + over;
-            if (acc + 0.5 * cu > target) break;
-            acc += cu;
-            u++;
-        }
+    for (int c = 0; c < n_cta; c++) {
         spans[c] = (int)u;
+        u += base + (c < rem ? 1 : 0);
     }
     spans[n_cta] = (int)units;
     int rc = alloc_dev(&e->d_spans, (size_t)n_cta + 1);
     if (rc) return rc;
     CK(cudaMemcpyAsync(e->d_spans, spans.data(), sizeof(int) * (n_cta + 1), cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));   // spans is a stack vector
-    e->span_key[0] = n_gt; e->span_key[1] = n_vt; e->span_key[2] = n_cta; e->span_key[3] = (int)(edge_cost * 1024);
+    e->span_key[0] = n_gt; e->span_key[1] = n_vt; e->span_key[2] = n_cta;
     e->graph_dirty = true;
     return NVB_OK;
 }
@@ -440,8 +441,7 @@ static int launch_dist_cfg2(nvb_engine *e, DistArgs da)
     const long long units = (long long)n_gt * n_vt;
     long long n_cta = (long long)e->sm_count * occ;
     if (n_cta > units) n_cta = units;
-    const double edge_cost = 1.0;   // every unit computes its full MG x MV tile
-    int rc = build_spans(e, n_gt, n_vt, edge_cost, (int)n_cta);
+    int rc = build_spans(e, n_gt, n_vt, (int)n_cta);
     if (rc) return rc;
     da.n_vt = n_vt;
     da.vt_per_split = 0;
@@ -455,28 +455,34 @@ static int launch_dist_cfg2(nvb_engine *e, DistArgs da)
 template <int TY, int MG, int MV, int CPR>
 static int launch_dist_cfg(nvb_engine *e, const DistArgs &da)
 {
-    // rows of exactly 16*CPR bytes with an odd chunk count: contiguous tiles, TMA bulk staging
-    if ((CPR % 2) == 1 && da.nk == 1 && da.Ppad == 16 * CPR && !getenv("NAVSIM_B200_NO_TMA"))
-        return launch_dist_cfg2<TY, MG, MV, CPR, true>(e, da);
-    return launch_dist_cfg2<TY, MG, MV, CPR, false>(e, da);
+    // odd chunk counts below 8 mean rows of exactly 16*CPR bytes (nk == 1): contiguous
+    // tiles, staged by TMA bulk copies; everything else goes through swizzled cp.async
+    constexpr bool BULK = (CPR % 2) == 1 && CPR < 8;
+    return launch_dist_cfg2<TY, MG, MV, CPR, BULK>(e, da);
 }
 
 template <int CPR>
 static int launch_dist_cpr(nvb_engine *e, const DistArgs &da)
 {
-    if (da.G <= 16) return launch_dist_cfg<1, 16, 2, CPR>(e, da);
-    if (da.G <= 64) return launch_dist_cfg<4, 8, 4, CPR>(e, da);
-    return launch_dist_cfg<16, 8, 8, CPR>(e, da);
+    if (da.G <= 16) return launch_dist_cfg<1, 16, 2, CPR>(e, da);      // 16 x 512 tiles: library streaming
+    if (da.G <= 64) return launch_dist_cfg<4, 8, 4, CPR>(e, da);       // 32 x 256
+    // many glimpses: 64-glimpse x 240- or 256-view tiles (4 x 15|16 sums per thread);
+    // the width that wastes fewer padded views wins
+    const long long pad15 = ((da.N + 239) / 240) * 240LL, pad16 = ((da.N + 255) / 256) * 256LL;
+    if (pad15 < pad16) return launch_dist_cfg<16, 4, 15, CPR>(e, da);
+    return launch_dist_cfg<16, 4, 16, CPR>(e, da);
 }
 
 // K2 over glimpses [0, G) of the engine's glimpse buffers; keys must be reset.
-static int launch_distance(nvb_engine *e, int G)
+static int launch_distance(nvb_engine *e, int G, bool bump_step = false)
 {
     DistArgs da;
     da.gv = e->d_gv; da.gh = e->d_gh; da.gs = e->d_gs;
     da.lv = e->d_lv; da.lh = e->d_lh; da.ls = e->d_ls;
     da.G = G; da.N = e->N; da.Ppad = e->Ppad; da.nk = e->nk;
     da.n_vt = 0; da.vt_per_split = 0; da.spans = nullptr;
+    da.step_counter = bump_step ? e->d_step : nullptr;
+    da.tie_count = bump_step ? e->d_tie_count : nullptr;
     da.view_offset = e->view_offset;
     da.keys = e->d_keys;
     da.cw = e->cw;
@@ -592,8 +598,8 @@ static int sample_poses(nvb_engine *e, const double *poses, const double *cs, in
     sa.status = d_status; sa.completed = nullptr; sa.budget = nullptr;
     sa.gv = pv; sa.gh = ph; sa.gs = ps;
     sa.keys = nullptr;
-    sa.step_counter = nullptr; sa.tie_count = nullptr;
     sa.band = sampler_band(e);
+    sa.dbg = nullptr;
     int rc = launch_sampler(e, sa, G);
     CK(cudaStreamSynchronize(e->stream));
     cudaFree(d_poses);
@@ -866,6 +872,7 @@ extern "C" int nvb_agents_set(nvb_engine *e, const double *poses, const int32_t 
         if ((rc = alloc_dev(&e->ag.coverage, (size_t)B * (e->n_path > 0 ? e->n_path : 1)))) return rc;
         if ((rc = alloc_dev(&e->d_poses0, (size_t)3 * B))) return rc;
         if ((rc = alloc_dev(&e->d_budget0, (size_t)B))) return rc;
+        if ((rc = alloc_dev(&e->d_pending, (size_t)B))) return rc;
         free_dev(e->log_best); free_dev(e->log_pose); free_dev(e->log_sfam); free_dev(e->log_afam);
         e->log_best = nullptr; e->log_pose = e->log_sfam = e->log_afam = nullptr;
         e->log_cap = 0;
@@ -890,6 +897,9 @@ extern "C" int nvb_agents_set(nvb_engine *e, const double *poses, const int32_t 
     CK(cudaMemsetAsync(e->ag.stepped, 0, sizeof(int32_t) * B, e->stream));
     CK(cudaMemsetAsync(e->ag.coverage, 0, (size_t)B * (e->n_path > 0 ? e->n_path : 1), e->stream));
     CK(cudaMemsetAsync(e->d_step, 0xFF, sizeof(int), e->stream));   // -1: first step bumps it to 0
+    CK(cudaMemsetAsync(e->d_pending, 0, sizeof(int32_t) * B, e->stream));
+    CK(cudaMemsetAsync(e->d_tie_ready, 0, sizeof(int) * (size_t)B * e->A, e->stream));   // epochs restart
+    e->glimpses_pending = false;
     CK(cudaMemsetAsync(e->d_tie_count, 0, sizeof(int), e->stream));
     e->steps_done = 0;
     CK(cudaStreamSynchronize(e->stream));
@@ -916,16 +926,19 @@ static StepArgs make_step_args(nvb_engine *e, int fake, int log_afam)
     s.threshold_factor = e->thf; s.coverage_factor = e->cvf;
     s.fake = fake;
     s.tie_count = e->d_tie_count; s.tie_items = e->d_tie_items; s.tie_thr = e->d_tie_thr;
+    s.tie_next = e->d_tie_next; s.tie_ready = e->d_tie_ready;
     s.step_counter = e->d_step;
     s.log_cap = e->log_cap;
     s.log_best = e->log_best; s.log_pose = e->log_pose; s.log_sfam = e->log_sfam;
     s.log_afam = log_afam ? e->log_afam : nullptr;
+    s.pending_fail = e->d_pending;
+    s.dbg = e->d_dbg;
     return s;
 }
 
 static int launch_distance_timed(nvb_engine *e, int G);
 
-static int phase1(nvb_engine *e)
+static SamplerArgs agent_sampler_args(nvb_engine *e)
 {
     SamplerArgs sa;
     sa.w = make_world(e);
@@ -934,11 +947,78 @@ static int phase1(nvb_engine *e)
     sa.status = e->ag.status; sa.completed = e->ag.completed; sa.budget = e->ag.budget;
     sa.gv = e->d_gv; sa.gh = e->d_gh; sa.gs = e->d_gs;
     sa.keys = e->d_keys;
-    sa.step_counter = e->d_step; sa.tie_count = e->d_tie_count;
     sa.band = sampler_band(e);
-    int rc = launch_sampler(e, sa, e->B);
-    if (rc) return rc;
+    sa.dbg = e->d_dbg;
+    return sa;
+}
+
+static int phase1(nvb_engine *e)
+{
+    if (!e->glimpses_pending) {
+        int rc = launch_sampler(e, agent_sampler_args(e), e->B);
+        if (rc) return rc;
+    }
+    e->glimpses_pending = false;
     return launch_distance_timed(e, e->B * e->A);
+}
+
+// decide + ties + move of this step and, in the same launch, the glimpses of the next
+template <bool HS, int PH, int PW>
+static int launch_k31_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa, size_t smem)
+{
+    static size_t attr_set[64] = {0};
+    size_t &cur = attr_set[e->device & 63];
+    if (smem > cur) {
+        CK(cudaFuncSetAttribute(k31_step_sample<HS, PH, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    k31_step_sample<HS, PH, PW><<<e->B, NVB_STEP_THREADS, smem, e->stream>>>(e->tmap, s, sa);
+    e->launches++;
+    CK(cudaGetLastError());
+    return NVB_OK;
+}
+
+template <bool HS, int PH, int PW>
+static int launch_k3ms_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa, size_t smem)
+{
+    static size_t attr_set[64] = {0};
+    size_t &cur = attr_set[e->device & 63];
+    if (smem > cur) {
+        CK(cudaFuncSetAttribute(k3_move_sample<HS, PH, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    k3_decide_help<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
+    k3_move_sample<HS, PH, PW><<<e->B, NVB_STEP_THREADS, smem, e->stream>>>(e->tmap, s, sa);
+    e->launches += 2;
+    CK(cudaGetLastError());
+    return NVB_OK;
+}
+
+// [decide + cooperative tie scan] then [move + sample next]
+static int launch_k3_split(nvb_engine *e, const StepArgs &s)
+{
+    const SamplerArgs sa = agent_sampler_args(e);
+    const int nplanes = sa.need_hs ? 3 : 1;
+    const size_t smem = e->R > 0 ? nvb_sampler_smem(e->BW, e->BH, nplanes, sa.A)
+                                 : nvb_sampler_smem(0, 0, 0, sa.A);
+    if (sa.need_hs) return launch_k3ms_t<true, 0, 0>(e, s, sa, smem);
+    if (e->ph == 4 && e->pw == 2) return launch_k3ms_t<false, 4, 2>(e, s, sa, smem);
+    if (e->ph == 2 && e->pw == 2) return launch_k3ms_t<false, 2, 2>(e, s, sa, smem);
+    if (e->ph == 1 && e->pw == 1) return launch_k3ms_t<false, 1, 1>(e, s, sa, smem);
+    return launch_k3ms_t<false, 0, 0>(e, s, sa, smem);
+}
+
+static int launch_k31(nvb_engine *e, const StepArgs &s)
+{
+    const SamplerArgs sa = agent_sampler_args(e);
+    const int nplanes = sa.need_hs ? 3 : 1;
+    const size_t smem = e->R > 0 ? nvb_sampler_smem(e->BW, e->BH, nplanes, sa.A)
+                                 : nvb_sampler_smem(0, 0, 0, sa.A);
+    if (sa.need_hs) return launch_k31_t<true, 0, 0>(e, s, sa, smem);
+    if (e->ph == 4 && e->pw == 2) return launch_k31_t<false, 4, 2>(e, s, sa, smem);
+    if (e->ph == 2 && e->pw == 2) return launch_k31_t<false, 2, 2>(e, s, sa, smem);
+    if (e->ph == 1 && e->pw == 1) return launch_k31_t<false, 1, 1>(e, s, sa, smem);
+    return launch_k31_t<false, 0, 0>(e, s, sa, smem);
 }
 
 static int phase2(nvb_engine *e, const StepArgs &s)
@@ -968,7 +1048,7 @@ static int check_step_ready(nvb_engine *e, int fake)
 // K2 with optional event timing around it
 static int launch_distance_timed(nvb_engine *e, int G)
 {
-    if (!e->timing) return launch_distance(e, G);
+    if (!e->timing) return launch_distance(e, G, true);
     if (e->ev_used + 2 > e->ev_pool.size()) {
         for (int i = 0; i < 64; i++) {
             cudaEvent_t ev;
@@ -977,7 +1057,7 @@ static int launch_distance_timed(nvb_engine *e, int G)
         }
     }
     CK(cudaEventRecord(e->ev_pool[e->ev_used], e->stream));
-    int rc = launch_distance(e, G);
+    int rc = launch_distance(e, G, true);
     CK(cudaEventRecord(e->ev_pool[e->ev_used + 1], e->stream));
     e->ev_used += 2;
     return rc;
@@ -988,17 +1068,34 @@ static int launch_distance_timed(nvb_engine *e, int G)
 // with the grid-wide tie pass.
 #define NVB_FUSED_STEP_MAX_VIEWS 65536
 
+static bool split_step()
+{
+    static const bool v = getenv("NAVSIM_B200_SPLIT_STEP") != nullptr;
+    return v;
+}
+
 static bool fused_step(const nvb_engine *e)
 {
     return e->view_offset == 0 && e->n_total == e->N && e->N <= NVB_FUSED_STEP_MAX_VIEWS &&
            !getenv("NAVSIM_B200_NO_FUSED_STEP");
 }
 
-static int one_step(nvb_engine *e, const StepArgs &s)
+// One step-batch.  Small un-sharded libraries (fused form): K2, then ONE launch that
+// decides, moves and already samples the next step's glimpses (sample_next) -- two
+// launches per step in steady state.  Otherwise: K1, K2, decide, ties, move.
+static int one_step(nvb_engine *e, const StepArgs &s, bool sample_next = true)
 {
     int rc;
     if ((rc = phase1(e))) return rc;
     if (fused_step(e)) {
+        if (sample_next) {
+            // measured on the 1024-agent workload: one fused launch (69 us/step) beats
+            // [decide + cooperative ties] + [move + sample] (79 us/step); the split form
+            // stays available as a tuning knob
+            if ((rc = split_step() ? launch_k3_split(e, s) : launch_k31(e, s))) return rc;
+            e->glimpses_pending = true;
+            return NVB_OK;
+        }
         k3_step<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
         e->launches++;
         CK(cudaGetLastError());
@@ -1040,21 +1137,28 @@ static int ensure_graph(nvb_engine *e, int fake, int log_afam)
 }
 
 
-static int run_steps(nvb_engine *e, int nsteps, int fake, int log_afam)
+// eager = plain launches, last step without sampling ahead (host-driven per-call use)
+static int run_steps(nvb_engine *e, int nsteps, int fake, int log_afam, bool eager = false)
 {
     int rc;
     if ((rc = ensure_log(e, e->steps_done + nsteps, log_afam != 0))) return rc;
-    if (e->use_graph && !e->timing) {
-        // first use of a configuration: run one step eagerly so that every
-        // cudaFuncSetAttribute / occupancy query happens outside stream capture
+    if (e->use_graph && !e->timing && !eager) {
         int done = 0;
         if (!graph_valid(e, fake, log_afam)) {
+            // first use of a configuration: one step with plain launches, so that every
+            // cudaFuncSetAttribute / occupancy query happens outside stream capture; in
+            // the fused form it also leaves the next step's glimpses sampled, which is the
+            // steady state the graph ({K2, step+sample}) is captured in
             const StepArgs s = make_step_args(e, fake, log_afam);
             if ((rc = one_step(e, s))) return rc;
             done = 1;
             if ((rc = ensure_graph(e, fake, log_afam))) return rc;
         }
-        const int per_step = fused_step(e) ? 3 : 5;   // K1, K2, step | K1, K2, decide, ties, move
+        if (done < nsteps && fused_step(e) && !e->glimpses_pending) {
+            if ((rc = launch_sampler(e, agent_sampler_args(e), e->B))) return rc;
+            e->glimpses_pending = true;
+        }
+        const int per_step = fused_step(e) ? (split_step() ? 3 : 2) : 5;   // K2, step+sample | K1, K2, decide, ties, move
         for (int i = done; i < nsteps; i++) {
             CK(cudaGraphLaunch(e->graph_exec, e->stream));
             e->launches += per_step;
@@ -1062,7 +1166,7 @@ static int run_steps(nvb_engine *e, int nsteps, int fake, int log_afam)
     } else {
         const StepArgs s = make_step_args(e, fake, log_afam);
         for (int i = 0; i < nsteps; i++)
-            if ((rc = one_step(e, s))) return rc;
+            if ((rc = one_step(e, s, !(eager && i == nsteps - 1)))) return rc;
     }
     e->steps_done += nsteps;
     return NVB_OK;
@@ -1091,6 +1195,9 @@ extern "C" int nvb_agents_rewind(nvb_engine *e)
     CK(cudaMemsetAsync(e->ag.err_n, 0, sizeof(int32_t) * B, e->stream));
     CK(cudaMemsetAsync(e->ag.coverage, 0, B * (e->n_path > 0 ? e->n_path : 1), e->stream));
     CK(cudaMemsetAsync(e->d_step, 0xFF, sizeof(int), e->stream));
+    CK(cudaMemsetAsync(e->d_pending, 0, sizeof(int32_t) * B, e->stream));
+    CK(cudaMemsetAsync(e->d_tie_ready, 0, sizeof(int) * (size_t)B * e->A, e->stream));   // epochs restart
+    e->glimpses_pending = false;
     e->steps_done = 0;
     return NVB_OK;
 }
@@ -1103,9 +1210,12 @@ extern "C" int nvb_agents_step_io(nvb_engine *e, const double *poses_in, int nst
     if (nsteps <= 0) return fail(NVB_E_INVALID, "nsteps must be positive");
     CK(cudaSetDevice(e->device));
     const size_t B = e->B;
-    if (poses_in)
+    if (poses_in) {
         CK(cudaMemcpyAsync(e->ag.poses, poses_in, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, e->stream));
-    if ((rc = run_steps(e, nsteps, 0, 0))) return rc;
+        CK(cudaMemsetAsync(e->d_pending, 0, sizeof(int32_t) * B, e->stream));
+        e->glimpses_pending = false;   // sampled for the old poses
+    }
+    if ((rc = run_steps(e, nsteps, 0, 0, poses_in != nullptr))) return rc;
     const size_t t = (size_t)e->steps_done - 1;
     if (best_idx)
         CK(cudaMemcpyAsync(best_idx, e->log_best + t * B, sizeof(int16_t) * B, cudaMemcpyDeviceToHost, e->stream));
@@ -1218,6 +1328,31 @@ extern "C" void *nvb_device_ptr(nvb_engine *e, int which)
 }
 
 // ---------------------------------------------------------------------------
+// Tuning aid: runs ONE step-batch with plain launches and returns, per agent, the
+// clock64 checkpoints of the fused step+sample kernel (start, active, decided,
+// moved, window requested, window landed, sampled; SM cycles).
+extern "C" int nvb_debug_step_clocks(nvb_engine *e, long long *out)
+{
+    int rc = check_step_ready(e, 0);
+    if (rc) return rc;
+    CK(cudaSetDevice(e->device));
+    CK(cudaMalloc(&e->d_dbg, sizeof(long long) * 8 * e->B));
+    CK(cudaMemsetAsync(e->d_dbg, 0, sizeof(long long) * 8 * e->B, e->stream));
+    rc = run_steps(e, 1, 0, 0, false);
+    if (!rc) {
+        const bool g = e->use_graph;
+        e->use_graph = false;
+        rc = run_steps(e, 1, 0, 0, false);
+        e->use_graph = g;
+    }
+    if (!rc) CK(cudaMemcpyAsync(out, e->d_dbg, sizeof(long long) * 8 * e->B, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_dbg);
+    e->d_dbg = nullptr;
+    e->graph_dirty = true;
+    return rc;
+}
+
 extern "C" double nvb_probe_sad_peak(nvb_engine *e, int iters)
 {
     if (cudaSetDevice(e->device) != cudaSuccess) return -1.0;

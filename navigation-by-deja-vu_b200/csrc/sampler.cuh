@@ -27,9 +27,8 @@ struct SamplerArgs {
     const int32_t *budget;     // agent mode: frame budget
     uint8_t *gv, *gh, *gs;   // [B*A][Ppad]
     unsigned long long *keys;  // [B*A] reset to "none" (agent mode) or nullptr
-    int *step_counter;       // agent mode: bumped once per step-batch (block 0), else nullptr
-    int *tie_count;          // agent mode: tie work list length, reset per step-batch
     float band;              // FP32 fast path: distance from a rounding tie below which FP64 decides
+    long long *dbg;          // optional [B][8] clock64 checkpoints (tuning aid), else nullptr
 };
 
 #define NVB_SAMPLER_THREADS 256
@@ -38,7 +37,7 @@ struct SamplerArgs {
 __host__ __device__ inline size_t nvb_sampler_smem(int BW, int BH, int nplanes, int A)
 {
     size_t win = (size_t)nvb_round_up(BW * BH, 128) * (size_t)nplanes;
-    return win + (size_t)A * 16 + 64;
+    return win + (size_t)A * 16 + 64 + 768;   // + mbarrier + quantisation tables
 }
 
 // Sample coordinates (util.pyx:159-168).  The reference evaluates
@@ -80,14 +79,79 @@ __device__ __noinline__ bool nvb_sample_exact(const SampleCtx &q, int col, int r
 #undef NVB_SAMPLER_THREADS
 #define NVB_SAMPLER_THREADS 128
 
+// Everything one sensor-pixel block needs besides the per-heading rotation.
+struct BlockCtx {
+    SampleCtx q;
+    const uint8_t *win_v, *win_h, *win_s;        // staged window planes (shared memory)
+    const uint8_t *land_v, *land_h, *land_s;     // landscape planes (global memory)
+    int use_win, ox, oy, BW, BH, pitch, ph, pw;
+    float xf, yf, tie;
+};
+
+// Careful path: per sample FP32 coordinate, exact FP64 on near-ties, wrap-around,
+// bounds (-> *err) and window tests.  Returns the V sum of the block; fills hh/ss
+// (hue / saturation samples) when NEED_HS.
 template <bool NEED_HS>
-__global__ void __launch_bounds__(NVB_SAMPLER_THREADS)
-k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
+__device__ __noinline__ int nvb_block_careful(const BlockCtx &c, float cf, float sf, int col0, int row0,
+                                              uint8_t *hh, uint8_t *ss, int *n_out, int *err)
 {
-    extern __shared__ __align__(128) uint8_t smem_k1[];
-    uint8_t *smem = smem_k1;
+    const SampleCtx &q = c.q;
+    const float px0 = (float)col0 - (float)q.half_w, py0 = (float)row0 - (float)q.half_h;
+    float tx_row = fmaf(px0, cf, fmaf(-py0, sf, c.xf));
+    float ty_row = fmaf(px0, sf, fmaf(py0, cf, c.yf));
+    int sum_v = 0, n = 0;
+    for (int i = 0; i < c.ph; i++) {
+        float tx = tx_row, ty = ty_row;
+        for (int j = 0; j < c.pw; j++) {
+            const float ux = tx + NVB_RND_MAGIC, uy = ty + NVB_RND_MAGIC;
+            const float dx = fabsf(tx - (ux - NVB_RND_MAGIC)), dy = fabsf(ty - (uy - NVB_RND_MAGIC));
+            tx += cf;
+            ty += sf;
+            int ix, iy;
+            if (fmaxf(dx, dy) < c.tie) {
+                ix = q.xi + (__float_as_int(ux) - NVB_RND_MAGIC_BITS);
+                iy = q.yi + (__float_as_int(uy) - NVB_RND_MAGIC_BITS);
+                if (ix < 0) ix += q.cols;
+                if (iy < 0) iy += q.rows;
+                if ((unsigned)ix >= (unsigned)q.cols || (unsigned)iy >= (unsigned)q.rows) {
+                    *err = 1;
+                    continue;
+                }
+            } else if (!nvb_sample_exact(q, col0 + j, row0 + i, ix, iy)) {
+                *err = 1;
+                continue;
+            }
+            const int lx = ix - c.ox, ly = iy - c.oy;
+            if (c.use_win && (unsigned)lx < (unsigned)c.BW && (unsigned)ly < (unsigned)c.BH) {
+                const int o = ly * c.BW + lx;
+                sum_v += c.win_v[o];
+                if (NEED_HS) { hh[n] = c.win_h[o]; ss[n] = c.win_s[o]; }
+            } else {
+                const size_t o = (size_t)iy * c.pitch + (size_t)ix;
+                sum_v += __ldg(c.land_v + o);
+                if (NEED_HS) { hh[n] = __ldg(c.land_h + o); ss[n] = __ldg(c.land_s + o); }
+            }
+            n++;
+        }
+        tx_row -= sf;
+        ty_row += cf;
+    }
+    *n_out = n;
+    return sum_v;
+}
+
+// Glimpses of one agent / pose at (x, y, ang): bounds test, TMA window, rotation
+// per heading, sampling, block reduce, quantise, mask.  Called by the whole CTA
+// (NVB_SAMPLER_THREADS threads).  A failing pose writes -2 (out of bounds,
+// NavBySceneFamiliarity.py:156-158) or -3 (IndexError, util.pyx:165-168) to
+// *fail_out and produces no (or partial) glimpses.
+// PH, PW: landscape pixels per sensor pixel known at compile time (0 = runtime).
+template <bool NEED_HS, int PH, int PW>
+__device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const SamplerArgs &a, int b,
+                                                double x, double y, double ang, uint8_t *smem,
+                                                int32_t *fail_out)
+{
     const NvbWorld &w = a.w;
-    const int b = blockIdx.x;
     const int tid = threadIdx.x;
     constexpr int nplanes = NEED_HS ? 3 : 1;
     const int use_win = (w.R > 0);
@@ -97,57 +161,40 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
     uint8_t *win_s = smem + 2 * plane_sz;
     double *cs_sm = (double *)(smem + plane_sz * nplanes);
     uint64_t *mbar = (uint64_t *)(cs_sm + 2 * a.A);
+    uint8_t *lut_sm = (uint8_t *)(mbar + 1);     // [3][256]
 
-    __shared__ int s_go;
     __shared__ int s_err;
 
-    const double x = a.poses[3 * b], y = a.poses[3 * b + 1], ang = a.poses[3 * b + 2];
-
-    if (tid == 0) {
-        int go = 1;
-        if (a.agent_mode) {
-            go = (a.status[b] == 0) && (a.completed[b] < a.budget[b]);
-        }
-        if (go) {
-            // NavBySceneFamiliarity.py:156-158
-            if (x <= w.r || y <= w.r || x >= (double)w.cols - w.r || y >= (double)w.rows - w.r) {
-                a.status[b] = -2;
-                go = 0;
-            } else if (!a.agent_mode) {
-                a.status[b] = 0;
-            }
-        }
-        s_go = go;
-        s_err = 0;
+    // NavBySceneFamiliarity.py:156-158 (every thread evaluates the same test)
+    if (x <= w.r || y <= w.r || x >= (double)w.cols - w.r || y >= (double)w.rows - w.r) {
+        if (tid == 0) *fail_out = -2;
+        return;
     }
-    if (a.keys != nullptr)
-        for (int k = tid; k < a.A; k += blockDim.x) a.keys[(size_t)b * a.A + k] = NVB_KEY_NONE;
-    if (a.step_counter != nullptr && b == 0 && tid == 0) {
-        // start of a step-batch: next log slot, empty tie list (nobody reads either
-        // before this kernel has finished)
-        *a.step_counter += 1;
-        *a.tie_count = 0;
-    }
-    __syncthreads();
-    if (!s_go) return;
-
     // TMA needs the box's innermost start coordinate on a 16-byte boundary (an
     // unaligned start traps with an illegal-instruction error on sm_100); BW has
     // 15 spare columns for that.
     const double fx = floor(x), fy = floor(y);
     const int xi = (int)fx, yi = (int)fy;
     const int ox = (xi - w.R) & ~15, oy = yi - w.R;
-    if (use_win && tid == 0) {
-        nvb_mbar_init(mbar, 1);
-        nvb_fence_barrier_init();
-        nvb_mbar_expect_tx(mbar, (uint32_t)(w.BW * w.BH * nplanes));
-        nvb_tma_load_3d(win_v, &tmap, ox, oy, 2, mbar);
-        if (NEED_HS) {
-            nvb_tma_load_3d(win_h, &tmap, ox, oy, 0, mbar);
-            nvb_tma_load_3d(win_s, &tmap, ox, oy, 1, mbar);
+    if (tid == 0) {
+        s_err = 0;
+        if (use_win) {
+            nvb_mbar_init(mbar, 1);
+            nvb_fence_barrier_init();
+            nvb_mbar_expect_tx(mbar, (uint32_t)(w.BW * w.BH * nplanes));
+            nvb_tma_load_3d(win_v, tmap, ox, oy, 2, mbar);
+            if (NEED_HS) {
+                nvb_tma_load_3d(win_h, tmap, ox, oy, 0, mbar);
+                nvb_tma_load_3d(win_s, tmap, ox, oy, 1, mbar);
+            }
         }
     }
-    // per-heading rotation, util.pyx:143-145
+    // while the window is in flight: quantisation tables -> shared memory, keys reset,
+    // per-heading rotation (util.pyx:143-145)
+    for (int k = tid; k < 768 / 4; k += blockDim.x)
+        reinterpret_cast<uint32_t *>(lut_sm)[k] = __ldg(reinterpret_cast<const uint32_t *>(w.lut) + k);
+    if (a.keys != nullptr)
+        for (int k = tid; k < a.A; k += blockDim.x) a.keys[(size_t)b * a.A + k] = NVB_KEY_NONE;
     for (int k = tid; k < a.A; k += blockDim.x) {
         double c, s;
         if (a.cs != nullptr) {
@@ -162,94 +209,79 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
         cs_sm[2 * k] = c;
         cs_sm[2 * k + 1] = s;
     }
+    if (a.dbg && tid == 0) a.dbg[b * 8 + 4] = clock64();
     __syncthreads();
     if (use_win) nvb_mbar_wait(mbar, 0);
+    if (a.dbg && tid == 0) a.dbg[b * 8 + 5] = clock64();
 
-    const uint8_t *land_h = w.land, *land_s = w.land + w.plane_stride,
-                  *land_v = w.land + 2 * w.plane_stride;
-    const int nblk = w.pw * w.ph;
-    SampleCtx q;
-    q.x = x; q.y = y;
-    q.half_w = 0.5 * (double)w.Wpx; q.half_h = 0.5 * (double)w.Hpx;
-    q.xi = xi; q.yi = yi;
-    q.band = a.band;
-    q.rows = w.rows; q.cols = w.cols;
-    const float xf = (float)(x - fx), yf = (float)(y - fy);
-    const float tie = 0.5f - a.band;
+    const int ph = PH ? PH : w.ph, pw = PW ? PW : w.pw;
+    const int nblk = pw * ph;
+    BlockCtx c;
+    c.q.x = x; c.q.y = y;
+    c.q.half_w = 0.5 * (double)w.Wpx; c.q.half_h = 0.5 * (double)w.Hpx;
+    c.q.xi = xi; c.q.yi = yi;
+    c.q.band = a.band;
+    c.q.rows = w.rows; c.q.cols = w.cols;
+    c.win_v = win_v; c.win_h = win_h; c.win_s = win_s;
+    c.land_h = w.land; c.land_s = w.land + w.plane_stride; c.land_v = w.land + 2 * w.plane_stride;
+    c.use_win = use_win; c.ox = ox; c.oy = oy; c.BW = w.BW; c.BH = w.BH; c.pitch = w.pitch;
+    c.ph = ph; c.pw = pw;
+    c.xf = (float)(x - fx); c.yf = (float)(y - fy);
+    c.tie = 0.5f - a.band;
     // `safe`: every sample of this agent lies inside the landscape and inside the
     // staged window (R = reach + 1), so no wrap / bounds / window test is needed
-    const bool safe = use_win && (xi - w.R >= 0) && (xi + w.R + 1 < w.cols) && (yi - w.R >= 0) &&
-                      (yi + w.R + 1 < w.rows);
-    const int wx0 = xi - ox, wy0 = yi - oy;   // window coordinates of (floor x, floor y)
+    const bool safe = !NEED_HS && use_win && (xi - w.R >= 0) && (xi + w.R + 1 < w.cols) &&
+                      (yi - w.R >= 0) && (yi + w.R + 1 < w.rows);
+    // window index of sample (lx, ly) relative to (floor x, floor y), with the magic-number
+    // bias of both float bit patterns folded in (32-bit wrap-around arithmetic is exact)
+    const int kbase = ((yi - oy) - NVB_RND_MAGIC_BITS) * w.BW + ((xi - ox) - NVB_RND_MAGIC_BITS);
+    const float inv_p = 1.0f / (float)w.P, inv_w = 1.0f / (float)w.W;
+    const float half_wf = (float)c.q.half_w, half_hf = (float)c.q.half_h;
     int err = 0;
 
     for (int it = tid; it < a.A * w.P; it += blockDim.x) {
-        const int k = it / w.P, p = it - k * w.P;
-        const int bi = p / w.W, bj = p - bi * w.W;
-        q.c = cs_sm[2 * k]; q.s = cs_sm[2 * k + 1];
-        const float cf = (float)q.c, sf = (float)q.s;
-        const int row0 = bi * w.ph, col0 = bj * w.pw;
-        const float px0 = (float)col0 - (float)q.half_w, py0 = (float)row0 - (float)q.half_h;
-        // coordinate of the block's first sample relative to (floor x, floor y)
-        float tx_row = fmaf(px0, cf, fmaf(-py0, sf, xf));
-        float ty_row = fmaf(px0, sf, fmaf(py0, cf, yf));
-        int sum_v = 0;
+        // it = k * P + bi * W + bj  (small integers: the float quotients are exact)
+        const int k = (int)(((float)it + 0.5f) * inv_p), p = it - k * w.P;
+        const int bi = (int)(((float)p + 0.5f) * inv_w), bj = p - bi * w.W;
+        c.q.c = cs_sm[2 * k]; c.q.s = cs_sm[2 * k + 1];
+        const float cf = (float)c.q.c, sf = (float)c.q.s;
+        const int row0 = bi * ph, col0 = bj * pw;
+        int sum_v = 0, n = 0;
         uint8_t hh[NEED_HS ? NVB_MAX_BLOCK_PX : 1], ss[NEED_HS ? NVB_MAX_BLOCK_PX : 1];
-        int n = 0;
-        for (int i = 0; i < w.ph; i++) {
-            float tx = tx_row, ty = ty_row;
-            for (int j = 0; j < w.pw; j++) {
-                const float ux = tx + NVB_RND_MAGIC, uy = ty + NVB_RND_MAGIC;
-                const float dx = fabsf(tx - (ux - NVB_RND_MAGIC)), dy = fabsf(ty - (uy - NVB_RND_MAGIC));
-                int lx = __float_as_int(ux) - NVB_RND_MAGIC_BITS, ly = __float_as_int(uy) - NVB_RND_MAGIC_BITS;
-                tx += cf;
-                ty += sf;
-                bool in_win;
-                if (fmaxf(dx, dy) < tie && safe) {
-                    lx += wx0;
-                    ly += wy0;
-                    in_win = true;
-                } else {
-                    int ix, iy;
-                    if (fmaxf(dx, dy) < tie) {
-                        ix = xi + lx;
-                        iy = yi + ly;
-                        if (ix < 0) ix += w.cols;
-                        if (iy < 0) iy += w.rows;
-                        if ((unsigned)ix >= (unsigned)w.cols || (unsigned)iy >= (unsigned)w.rows) {
-                            err = 1;
-                            continue;
-                        }
-                    } else if (!nvb_sample_exact(q, col0 + j, row0 + i, ix, iy)) {
-                        err = 1;
-                        continue;
-                    }
-                    lx = ix - ox;
-                    ly = iy - oy;
-                    in_win = use_win && (unsigned)lx < (unsigned)w.BW && (unsigned)ly < (unsigned)w.BH;
-                    if (!in_win) {
-                        const size_t o = (size_t)iy * w.pitch + (size_t)ix;
-                        sum_v += __ldg(land_v + o);
-                        if (NEED_HS) { hh[n] = __ldg(land_h + o); ss[n] = __ldg(land_s + o); }
-                    }
+        bool done = false;
+        if (safe) {
+            // lean path: no branches; the largest distance from a rounding tie seen in
+            // the block decides afterwards whether the careful path must redo it
+            // (sm_100 packed FP32x2: x and y coordinate advance, round and compare together)
+            const float px0 = (float)col0 - half_wf, py0 = (float)row0 - half_hf;
+            float2 t_row = make_float2(fmaf(px0, cf, fmaf(-py0, sf, c.xf)), fmaf(px0, sf, fmaf(py0, cf, c.yf)));
+            const float2 step_j = make_float2(cf, sf), step_i = make_float2(-sf, cf);
+            const float2 magic = make_float2(NVB_RND_MAGIC, NVB_RND_MAGIC);
+            const float2 neg_magic = make_float2(-NVB_RND_MAGIC, -NVB_RND_MAGIC), neg_one = make_float2(-1.0f, -1.0f);
+            float worst = 0.0f;
+#pragma unroll
+            for (int i = 0; i < ph; i++) {
+                float2 t = t_row;
+#pragma unroll
+                for (int j = 0; j < pw; j++) {
+                    const float2 u = __fadd2_rn(t, magic);                     // low mantissa bits = round(t)
+                    const float2 e = __ffma2_rn(__fadd2_rn(u, neg_magic), neg_one, t);   // t - round(t)
+                    worst = fmaxf(worst, fmaxf(fabsf(e.x), fabsf(e.y)));
+                    sum_v += win_v[__float_as_int(u.y) * w.BW + __float_as_int(u.x) + kbase];
+                    t = __fadd2_rn(t, step_j);
                 }
-                if (in_win) {
-                    const int o = ly * w.BW + lx;
-                    sum_v += win_v[o];
-                    if (NEED_HS) { hh[n] = win_h[o]; ss[n] = win_s[o]; }
-                }
-                n++;
+                t_row = __fadd2_rn(t_row, step_i);
             }
-            tx_row -= sf;
-            ty_row += cf;
+            done = worst < c.tie;
         }
+        if (!done) sum_v = nvb_block_careful<NEED_HS>(c, cf, sf, col0, row0, hh, ss, &n, &err);
         // util.pyx:121-123: V = (uint8) round(sum / (fr*fc)), half away from zero.  In
         // integers: the quotient is either an exact tie or at least 1/(2*fr*fc) away
         // from one, far more than the FP64 division's rounding.
         uint8_t v = (uint8_t)((2 * sum_v + nblk) / (2 * nblk));
         const bool masked = (bj >= w.mask_lo && bj < w.mask_hi);   // NavBySceneFamiliarity.py:189-190
         const size_t o = ((size_t)b * a.A + k) * w.Ppad + p;
-        a.gv[o] = masked ? 0 : w.lut[512 + v];
+        a.gv[o] = masked ? 0 : lut_sm[512 + v];
         if (NEED_HS) {
             // util.pyx:126-132: hue with the largest summed S (strict >, so the
             // lowest hue wins ties and hue 0 wins when every sum is 0);
@@ -266,14 +298,31 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
                     best_h = hh[t];
                 }
             }
-            const uint8_t sat = (uint8_t)((best_sum / w.ph) * w.pw);
-            a.gh[o] = masked ? 0 : w.lut[best_h];
-            a.gs[o] = masked ? 0 : w.lut[256 + sat];
+            const uint8_t sat = (uint8_t)((best_sum / ph) * pw);
+            a.gh[o] = masked ? 0 : lut_sm[best_h];
+            a.gs[o] = masked ? 0 : lut_sm[256 + sat];
         }
     }
     if (err) s_err = 1;
     __syncthreads();
-    if (tid == 0 && s_err) a.status[b] = -3;   // IndexError, util.pyx:165-168
+    if (tid == 0 && s_err) *fail_out = -3;   // IndexError, util.pyx:165-168
+    if (a.dbg && tid == 0) a.dbg[b * 8 + 6] = clock64();
+}
+
+// K1 as its own launch: one CTA per agent (resident loop) or per pose (A == 1).
+template <bool NEED_HS, int PH, int PW>
+__global__ void __launch_bounds__(NVB_SAMPLER_THREADS)
+k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem_k1[];
+    const int b = blockIdx.x;
+    if (a.agent_mode) {
+        if (!(a.status[b] == 0 && a.completed[b] < a.budget[b])) return;
+    } else if (threadIdx.x == 0) {
+        a.status[b] = 0;
+    }
+    nvb_sample_body<NEED_HS, PH, PW>(&tmap, a, b, a.poses[3 * b], a.poses[3 * b + 1], a.poses[3 * b + 2],
+                                     smem_k1, a.status + b);
 }
 
 // planar [G][Ppad] x3 -> interleaved [G][P][3] (familiar_scenes / get_sensor_mat layout)

@@ -20,6 +20,7 @@
 #pragma once
 #include "common.cuh"
 #include "distance.cuh"
+#include "sampler.cuh"
 
 struct AgentState {
     double *poses;          // [B][3]
@@ -47,7 +48,7 @@ struct StepArgs {
     int idx_bits;
     unsigned long long band;     // score band treated as tied (0 for chem_weight == 0)
     double cw;
-    const double *div255;
+    const double *div255;        // [256] k / 255.
     double maxfam;               // H*W
     double step_size, max_dist, threshold_factor, coverage_factor;
     int fake;
@@ -55,6 +56,8 @@ struct StepArgs {
     int *tie_count;
     int2 *tie_items;             // (glimpse index, unused)
     unsigned long long *tie_thr; // per item: largest score still treated as tied
+    int *tie_next;               // per item: next unclaimed view chunk (k3_decide_help)
+    int *tie_ready;              // per item: step index + 1 once the item is published
     // log
     const int *step_counter;     // device step index
     int log_cap;
@@ -62,9 +65,17 @@ struct StepArgs {
     double *log_pose;            // [cap][B][3]
     double *log_sfam;            // [cap][B]
     double *log_afam;            // [cap][B][A] or nullptr
+    int32_t *pending_fail;       // [B] failure the sampler found for the NEXT step, or nullptr
+    long long *dbg;              // tuning aid (see SamplerArgs::dbg), else nullptr
 };
 
-#define NVB_STEP_THREADS 128
+#define NVB_STEP_THREADS 128   /* == NVB_SAMPLER_THREADS: k31_step_sample runs both bodies */
+#define NVB_STEP_MAX_A_SMEM 512 /* headings whose exact differences are kept in shared memory */
+#define NVB_TIE_Q_CHUNKS 64     /* fused tie scan: glimpse rows up to 1 KB are staged in shared memory */
+#define NVB_TIE_VPT 6           /* fused tie scan: views per thread in flight */
+
+// {k / 255.} for k in 0..255 (util.pyx:71): a.div255 in global memory, staged per CTA in
+// shared memory (the lookups are divergent: constant memory would serialise them)
 
 __device__ __forceinline__ bool nvb_agent_active(const AgentState &ag, int b)
 {
@@ -74,22 +85,31 @@ __device__ __forceinline__ bool nvb_agent_active(const AgentState &ag, int b)
 // Exact FP64 difference with 16-byte row loads (rows are 16-B aligned and zero
 // padded; a zero pad pixel adds +0.0, which leaves the sum unchanged).
 __device__ __forceinline__ double nvb_exact_diff_rows(const StepArgs &a, size_t qo, size_t fo,
-                                                      const double *div255)
+                                                      const double *c_div255)
 {
     if (a.cw != 0.0)
         return nvb_exact_diff(a.gh + qo, a.gs + qo, a.gv + qo, a.lh + fo, a.ls + fo, a.lv + fo, a.P,
-                              a.cw, div255);
+                              a.cw, c_div255);
     const uint4 *q = reinterpret_cast<const uint4 *>(a.gv + qo);
     const uint4 *f = reinterpret_cast<const uint4 *>(a.lv + fo);
     double diff = 0.0;
-    for (int c = 0; c < a.Ppad / 16; c++) {
-        const uint4 qq = q[c], ff = __ldg(f + c);
-        const uint32_t d[4] = {__vabsdiffu4(qq.x, ff.x), __vabsdiffu4(qq.y, ff.y),
-                               __vabsdiffu4(qq.z, ff.z), __vabsdiffu4(qq.w, ff.w)};
+    const int nc = a.Ppad / 16;
+    for (int c0 = 0; c0 < nc; c0 += 4) {
+        // up to four 16-B chunks of both rows in flight before the dependent FP64 chain
+        uint4 qq[4], ff[4];
 #pragma unroll
-        for (int w = 0; w < 4; w++)
+        for (int u = 0; u < 4; u++)
+            if (c0 + u < nc) { qq[u] = q[c0 + u]; ff[u] = __ldg(f + c0 + u); }
 #pragma unroll
-            for (int k = 0; k < 4; k++) diff = __dadd_rn(diff, div255[(d[w] >> (8 * k)) & 0xFFu]);
+        for (int u = 0; u < 4; u++)
+            if (c0 + u < nc) {
+                const uint32_t d[4] = {__vabsdiffu4(qq[u].x, ff[u].x), __vabsdiffu4(qq[u].y, ff[u].y),
+                                       __vabsdiffu4(qq[u].z, ff[u].z), __vabsdiffu4(qq[u].w, ff[u].w)};
+#pragma unroll
+                for (int w = 0; w < 4; w++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) diff = __dadd_rn(diff, c_div255[(d[w] >> (8 * k)) & 0xFFu]);
+            }
     }
     return diff;
 }
@@ -117,26 +137,48 @@ __device__ __forceinline__ unsigned long long nvb_pair_score(const StepArgs &a, 
 
 // decide: exact difference of every heading's best view and detection of headings
 // tied at the step's minimum.  FUSED: the CTA scans the library for its tied
-// headings right away; otherwise they go to the work list of k3_ties.
+// headings right away; otherwise they go to the work list of k3_ties.  The exact
+// differences end up in a.exact (global) and, for A <= NVB_STEP_MAX_A_SMEM, in
+// s_exact (shared) for the move that follows in the same CTA.
 template <bool FUSED>
-__device__ __forceinline__ void nvb_decide(const StepArgs &a, int b, const double *div255)
+__device__ __forceinline__ void nvb_decide(const StepArgs &a, int b, unsigned long long *s_exact,
+                                           const double *div255)
 {
     const int tid = threadIdx.x;
     __shared__ unsigned long long s_min;
     __shared__ int s_ntied;
-    if (tid == 0) { s_min = ~0ull; s_ntied = 0; }
-    __syncthreads();
     const unsigned long long idx_mask = (1ull << a.idx_bits) - 1ull;
-    unsigned long long local = ~0ull;
-    for (int k = tid; k < a.A; k += blockDim.x)
-        local = min(local, a.keys[(size_t)b * a.A + k] >> a.idx_bits);
-    if (local != ~0ull) atomicMin(&s_min, local);
-    __syncthreads();
-    const unsigned long long thr = s_min + a.band;
-    for (int k = tid; k < a.A; k += blockDim.x)
-        if ((a.keys[(size_t)b * a.A + k] >> a.idx_bits) <= thr) atomicAdd(&s_ntied, 1);
-    __syncthreads();
-    const bool have_ties = s_ntied > 1;
+    const bool small = a.A <= 32;
+    unsigned long long thr;
+    bool have_ties;
+    if (small) {
+        // one warp holds every key: minimum and tie count by shuffles, broadcast through
+        // shared memory with a single barrier
+        if (tid < 32) {
+            const unsigned long long sc =
+                (tid < a.A) ? (a.keys[(size_t)b * a.A + tid] >> a.idx_bits) : ~0ull;
+            unsigned long long m = sc;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+            const unsigned nt = __popc(__ballot_sync(0xFFFFFFFFu, sc <= m + a.band));
+            if (tid == 0) { s_min = m; s_ntied = (int)nt; }
+        }
+        __syncthreads();
+    } else {
+        if (tid == 0) { s_min = ~0ull; s_ntied = 0; }
+        __syncthreads();
+        unsigned long long local = ~0ull;
+        for (int k = tid; k < a.A; k += blockDim.x)
+            local = min(local, a.keys[(size_t)b * a.A + k] >> a.idx_bits);
+        if (local != ~0ull) atomicMin(&s_min, local);
+        __syncthreads();
+        const unsigned long long t = s_min + a.band;
+        for (int k = tid; k < a.A; k += blockDim.x)
+            if ((a.keys[(size_t)b * a.A + k] >> a.idx_bits) <= t) atomicAdd(&s_ntied, 1);
+        __syncthreads();
+    }
+    thr = s_min + a.band;
+    have_ties = s_ntied > 1;
     for (int k = tid; k < a.A; k += blockDim.x) {
         const size_t g = (size_t)b * a.A + k;
         const unsigned long long key = a.keys[g];
@@ -149,7 +191,8 @@ __device__ __forceinline__ void nvb_decide(const StepArgs &a, int b, const doubl
                 ebits = (unsigned long long)__double_as_longlong(d);
             }
         }
-        a.exact[g] = ebits;
+        if (FUSED && k < NVB_STEP_MAX_A_SMEM) s_exact[k] = ebits;
+        if (!FUSED || k >= NVB_STEP_MAX_A_SMEM || have_ties) a.exact[g] = ebits;
         if (!FUSED && tied) {
             const int slot = atomicAdd(a.tie_count, 1);
             a.tie_items[slot] = make_int2((int)g, 0);
@@ -158,28 +201,89 @@ __device__ __forceinline__ void nvb_decide(const StepArgs &a, int b, const doubl
     }
     if (FUSED && have_ties) {
         __syncthreads();   // exact[] initialised
+        __shared__ uint4 s_q[NVB_TIE_Q_CHUNKS];
+        const int nc = a.Ppad / 16;
+        const bool fast = (a.cw == 0.0) && nc <= NVB_TIE_Q_CHUNKS;
         for (int k = 0; k < a.A; k++) {
             const size_t g = (size_t)b * a.A + k;
             if ((a.keys[g] >> a.idx_bits) > thr) continue;   // CTA-uniform
-            for (int v = tid; v < a.N; v += blockDim.x) {
-                if (nvb_pair_score(a, g * a.Ppad, (size_t)v * a.Ppad) <= thr) {
-                    const double d = nvb_exact_diff_rows(a, g * a.Ppad, (size_t)v * a.Ppad, div255);
-                    atomicMin(a.exact + g, (unsigned long long)__double_as_longlong(d));
+            if (fast) {
+                // glimpse row in shared memory (broadcast reads); two views per thread in
+                // flight, 16-byte loads: the scan is bound by L2 latency, not arithmetic
+                __syncthreads();
+                for (int c = tid; c < nc; c += blockDim.x) s_q[c] = reinterpret_cast<const uint4 *>(a.gv + g * a.Ppad)[c];
+                __syncthreads();
+                // NVB_TIE_VPT views per thread at a time, chunk by chunk: every load of a
+                // chunk is in flight before the first sum needs it
+                for (int v0 = 0; v0 < a.N; v0 += NVB_TIE_VPT * NVB_STEP_THREADS) {
+                    uint32_t sum[NVB_TIE_VPT];
+                    const uint4 *fp[NVB_TIE_VPT];
+#pragma unroll
+                    for (int u = 0; u < NVB_TIE_VPT; u++) {
+                        const int v = v0 + u * NVB_STEP_THREADS + tid;
+                        fp[u] = reinterpret_cast<const uint4 *>(a.lv + (size_t)(v < a.N ? v : 0) * a.Ppad);
+                        sum[u] = 0;
+                    }
+                    for (int c = 0; c < nc; c++) {
+                        uint4 x[NVB_TIE_VPT];
+#pragma unroll
+                        for (int u = 0; u < NVB_TIE_VPT; u++) x[u] = __ldg(fp[u] + c);
+                        const uint4 q = s_q[c];
+#pragma unroll
+                        for (int u = 0; u < NVB_TIE_VPT; u++) {
+                            sum[u] = nvb_sad4(q.x, x[u].x, sum[u]); sum[u] = nvb_sad4(q.y, x[u].y, sum[u]);
+                            sum[u] = nvb_sad4(q.z, x[u].z, sum[u]); sum[u] = nvb_sad4(q.w, x[u].w, sum[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < NVB_TIE_VPT; u++) {
+                        const int v = v0 + u * NVB_STEP_THREADS + tid;
+                        if (v < a.N && sum[u] <= thr) {
+                            if (a.dbg) atomicAdd((unsigned long long *)a.dbg + b * 8 + 7, 1ull);
+                            const double d = nvb_exact_diff_rows(a, g * a.Ppad, (size_t)v * a.Ppad, div255);
+                            atomicMin(a.exact + g, (unsigned long long)__double_as_longlong(d));
+                        }
+                    }
+                }
+            } else {
+                for (int v = tid; v < a.N; v += blockDim.x) {
+                    if (nvb_pair_score(a, g * a.Ppad, (size_t)v * a.Ppad) <= thr) {
+                        const double d = nvb_exact_diff_rows(a, g * a.Ppad, (size_t)v * a.Ppad, div255);
+                        atomicMin(a.exact + g, (unsigned long long)__double_as_longlong(d));
+                    }
                 }
             }
         }
+        __syncthreads();
+        for (int k = tid; k < a.A && k < NVB_STEP_MAX_A_SMEM; k += blockDim.x)
+            if ((a.keys[(size_t)b * a.A + k] >> a.idx_bits) <= thr) s_exact[k] = a.exact[(size_t)b * a.A + k];
     }
 }
 
-// move: argmax, pose update, update_error, end test, log.  Requires a.exact final.
-__device__ __forceinline__ void nvb_move(const StepArgs &a, int b)
+// move: argmax, pose update, update_error, end test, log.  s_exact (shared, may be
+// nullptr) / a.exact hold the exact differences.  Returns through *pose_out the
+// new pose and whether the agent will take another step (status still 0 and
+// budget left); every thread gets the same answer.
+__device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigned long long *s_exact,
+                                         double *pose_out)
 {
     const int tid = threadIdx.x;
     const int t = *a.step_counter;
     const bool logging = (t >= 0 && t < a.log_cap);
-    __shared__ int s_go;
-    __shared__ double s_x, s_y;
+    __shared__ int s_go, s_more;
+    __shared__ double s_pose[3];
     __shared__ double s_red[NVB_STEP_THREADS / 32];
+
+    // counters the bookkeeping at the end needs: loaded early, used late
+    int nav_frames = 0, err_n = 0, completed = 0, budget = 0;
+    double err_sum = 0.0;
+    if (tid == 0) {
+        nav_frames = a.ag.nav_frames[b];
+        err_n = a.ag.err_n[b];
+        err_sum = a.ag.err_sum[b];
+        completed = a.ag.completed[b];
+        budget = a.ag.budget[b];
+    }
 
     if (tid == 0) {
         // angle_familiarity[k] = maxfam - diff (util.pyx:73, NavBySceneFamiliarity.py:313);
@@ -187,8 +291,9 @@ __device__ __forceinline__ void nvb_move(const StepArgs &a, int b)
         int best = 0;
         double best_fam = 0.0;
         for (int k = 0; k < a.A; k++) {
-            const double d = __longlong_as_double((long long)a.exact[(size_t)b * a.A + k]);
-            const double fam = __dsub_rn(a.maxfam, d);
+            const unsigned long long eb =
+                (s_exact != nullptr && k < NVB_STEP_MAX_A_SMEM) ? s_exact[k] : a.exact[(size_t)b * a.A + k];
+            const double fam = __dsub_rn(a.maxfam, __longlong_as_double((long long)eb));
             if (logging && a.log_afam) a.log_afam[((size_t)t * a.B + b) * a.A + k] = fam;
             if (k == 0 || fam > best_fam) { best = k; best_fam = fam; }
         }
@@ -201,8 +306,7 @@ __device__ __forceinline__ void nvb_move(const StepArgs &a, int b)
         a.ag.poses[3 * b] = x;
         a.ag.poses[3 * b + 1] = y;
         a.ag.poses[3 * b + 2] = ang;
-        s_x = x;
-        s_y = y;
+        s_pose[0] = x; s_pose[1] = y; s_pose[2] = ang;
         if (logging) {
             a.log_best[(size_t)t * a.B + b] = (int16_t)best;
             a.log_pose[((size_t)t * a.B + b) * 3] = x;
@@ -210,20 +314,36 @@ __device__ __forceinline__ void nvb_move(const StepArgs &a, int b)
             a.log_pose[((size_t)t * a.B + b) * 3 + 2] = ang;
             a.log_sfam[(size_t)t * a.B + b] = best_fam;
         }
-        if (a.fake) a.ag.completed[b] += 1;
+        if (a.fake) {
+            a.ag.completed[b] = completed + 1;
+            s_more = (completed + 1 < budget);
+        }
     }
     __syncthreads();
-    if (a.fake) return;
+    pose_out[0] = s_pose[0]; pose_out[1] = s_pose[1]; pose_out[2] = s_pose[2];
+    if (a.fake) return s_more != 0;
 
-    // update_error, :252-276.  min over sqrt(d2) == sqrt(min d2) (sqrt is monotone
-    // and correctly rounded), so reduce d2 and take one sqrt.
-    const double x = s_x, y = s_y;
+    // update_error, :252-276.  min over sqrt(d2) == sqrt(min d2) (sqrt is monotone and
+    // correctly rounded), so reduce d2 and take one sqrt.  Coverage (:272-276) marks
+    // every point with d <= thr when dmin <= thr; a point with d <= thr implies
+    // dmin <= thr, so when thr <= max_dist (no TooFar possible then) it is marked in
+    // the same pass, comparing d2 with thr2 = the largest double whose sqrt is <= thr.
+    const double x = s_pose[0], y = s_pose[1];
+    const double thr = __dmul_rn(a.coverage_factor, a.step_size);   // :271
+    double thr2 = __dmul_rn(thr, thr);
+    while (__dsqrt_rn(thr2) > thr) thr2 = __longlong_as_double(__double_as_longlong(thr2) - 1);
+    while (__dsqrt_rn(__longlong_as_double(__double_as_longlong(thr2) + 1)) <= thr)
+        thr2 = __longlong_as_double(__double_as_longlong(thr2) + 1);
+    const bool one_pass = thr <= a.max_dist;
     const double2 *path = reinterpret_cast<const double2 *>(a.path);
     double m = __longlong_as_double(0x7FF0000000000000ll);
-    for (int n = tid; n < a.n_path; n += blockDim.x) {
+#pragma unroll 4
+    for (int n = tid; n < a.n_path; n += NVB_STEP_THREADS) {
         const double2 pt = __ldg(path + n);
         const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
-        m = fmin(m, __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        m = fmin(m, d2);
+        if (one_pass && d2 <= thr2) a.ag.coverage[(size_t)b * a.n_path + n] = 1;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
@@ -233,39 +353,39 @@ __device__ __forceinline__ void nvb_move(const StepArgs &a, int b)
 #pragma unroll
     for (int wq = 1; wq < NVB_STEP_THREADS / 32; wq++) m = fmin(m, s_red[wq]);
     const double dmin = __dsqrt_rn(m);
-    const double thr = __dmul_rn(a.coverage_factor, a.step_size);   // :271
     if (tid == 0) {
-        int go = 1;
-        a.ag.nav_frames[b] += 1;                                    // :253
+        int go = 1, more = 0;
+        a.ag.nav_frames[b] = nav_frames + 1;                        // :253
         if (dmin > a.max_dist) {                                    // :263-264
             a.ag.status[b] = -1;
             go = 0;
         } else {
-            a.ag.err_sum[b] = __dadd_rn(a.ag.err_sum[b], __dmul_rn(dmin, dmin));   // :267
-            a.ag.err_n[b] += 1;                                                    // :268
+            a.ag.err_sum[b] = __dadd_rn(err_sum, __dmul_rn(dmin, dmin));   // :267
+            a.ag.err_n[b] = err_n + 1;                                     // :268
+            // :328 end-of-path test
+            const double2 pe = __ldg(path + (a.n_path - 1));
+            const double ex = __dsub_rn(pe.x, x), ey = __dsub_rn(pe.y, y);
+            const double de = __dsqrt_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
+            if (de <= __dmul_rn(a.threshold_factor, a.step_size)) {
+                a.ag.status[b] = 1;
+            } else {
+                a.ag.completed[b] = completed + 1;
+                more = (completed + 1 < budget);
+            }
         }
         s_go = go;
+        s_more = more;
     }
     __syncthreads();
-    if (!s_go) return;
-    if (dmin <= thr) {                                              // :272-276
-        for (int n = tid; n < a.n_path; n += blockDim.x) {
+    if (s_go && !one_pass && dmin <= thr) {                         // :272-276, two-pass form
+        for (int n = tid; n < a.n_path; n += NVB_STEP_THREADS) {
             const double2 pt = __ldg(path + n);
             const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
-            const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-            if (d <= thr) a.ag.coverage[(size_t)b * a.n_path + n] = 1;
+            if (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= thr2)
+                a.ag.coverage[(size_t)b * a.n_path + n] = 1;
         }
     }
-    if (tid == 0) {
-        // :328 end-of-path test
-        const double2 pe = __ldg(path + (a.n_path - 1));
-        const double ex = __dsub_rn(pe.x, x), ey = __dsub_rn(pe.y, y);
-        const double de = __dsqrt_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
-        if (de <= __dmul_rn(a.threshold_factor, a.step_size))
-            a.ag.status[b] = 1;
-        else
-            a.ag.completed[b] += 1;
-    }
+    return s_more != 0;
 }
 
 // log entry of an agent that does not take part in this step
@@ -284,40 +404,246 @@ __device__ __forceinline__ void nvb_log_idle(const StepArgs &a, int b)
         for (int k = tid; k < a.A; k += blockDim.x) a.log_afam[((size_t)t * a.B + b) * a.A + k] = nan;
 }
 
-__device__ __forceinline__ void nvb_load_div255(const StepArgs &a, double *s_div)
+// A failure the sampler found for THIS step while it ran at the end of the previous
+// launch (k31_step_sample) becomes the agent's status now, at the step it belongs to.
+__device__ __forceinline__ void nvb_commit_pending(const StepArgs &a, int b)
 {
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_div[k] = a.div255[k];
+    if (a.pending_fail != nullptr && threadIdx.x == 0) {
+        const int pf = a.pending_fail[b];
+        if (pf != 0) {
+            a.ag.status[b] = pf;
+            a.pending_fail[b] = 0;
+        }
+    }
     __syncthreads();
 }
 
 // ---- one launch: decide + ties + move ------------------------------------------
-__global__ void __launch_bounds__(NVB_STEP_THREADS)
+__global__ void __launch_bounds__(NVB_STEP_THREADS, 8)
 k3_step(StepArgs a)
 {
+    __shared__ unsigned long long s_exact[NVB_STEP_MAX_A_SMEM];
     __shared__ double s_div[256];
     const int b = blockIdx.x;
-    // an agent K1 stopped in this step (out of bounds / index error) is no longer active
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_div[k] = a.div255[k];
+    nvb_commit_pending(a, b);
+    // an agent the sampler stopped in this step (out of bounds / index error) is no longer active
     if (!nvb_agent_active(a.ag, b)) {
         nvb_log_idle(a, b);
         return;
     }
-    nvb_load_div255(a, s_div);
-    nvb_decide<true>(a, b, s_div);
+    nvb_decide<true>(a, b, s_exact, s_div);
     __syncthreads();
-    nvb_move(a, b);
+    double pose[3];
+    nvb_move(a, b, s_exact, pose);
+}
+
+// ---- one launch: decide + ties + move of step t, then the glimpses of step t+1 ----
+// (the sampler's failures for step t+1 are parked in a.pending_fail until then)
+template <bool NEED_HS, int PH, int PW>
+__global__ void __launch_bounds__(NVB_STEP_THREADS, 8)   // 1024 agents = 7 CTAs per SM: one wave
+k31_step_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs sa)
+{
+    extern __shared__ __align__(128) uint8_t smem_k31[];
+    __shared__ unsigned long long s_exact[NVB_STEP_MAX_A_SMEM];
+    __shared__ double s_div[256];
+    const int b = blockIdx.x;
+    if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 0] = clock64();
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_div[k] = a.div255[k];
+    nvb_commit_pending(a, b);
+    if (!nvb_agent_active(a.ag, b)) {
+        nvb_log_idle(a, b);
+        return;
+    }
+    if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 1] = clock64();
+    nvb_decide<true>(a, b, s_exact, s_div);
+    __syncthreads();
+    if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 2] = clock64();
+    double pose[3];
+    const bool more = nvb_move(a, b, s_exact, pose);
+    if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 3] = clock64();
+    if (!more) return;
+    __syncthreads();
+    nvb_sample_body<NEED_HS, PH, PW>(&tmap, sa, b, pose[0], pose[1], pose[2], smem_k31, a.pending_fail + b);
+}
+
+// ---- two launches: [decide + cooperative tie scan] then [move + sample] ------------
+// Ties hit a few agents per step, but each needs a rescan of the whole library for
+// its tied headings: far too much for one CTA while a thousand others sit idle.
+// So every CTA first decides for its own agent, publishes its tied headings to a
+// queue, and then helps: view chunks of queued items are claimed with an atomic
+// counter by whichever CTA gets there.  The owner always sweeps its own items to
+// the end, so every chunk is scanned by the time the kernel completes; the kernel
+// boundary is the barrier before k3_move_sample reads the exact differences.
+#define NVB_HELP_CHUNK (2 * NVB_STEP_THREADS)   /* views per claimed chunk */
+#define NVB_HELP_BUDGET 2                       /* chunks a helping CTA scans at most */
+
+__device__ __forceinline__ void nvb_tie_scan_chunk(const StepArgs &a, int g, unsigned long long thr,
+                                                   int chunk, const double *div255)
+{
+    const int nc = a.Ppad / 16;
+    const size_t qo = (size_t)g * a.Ppad;
+    const int v0 = chunk * NVB_HELP_CHUNK + threadIdx.x, v1 = v0 + NVB_STEP_THREADS;
+    if (a.cw == 0.0) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(a.gv + qo);
+        const uint4 *f0 = reinterpret_cast<const uint4 *>(a.lv + (size_t)(v0 < a.N ? v0 : 0) * a.Ppad);
+        const uint4 *f1 = reinterpret_cast<const uint4 *>(a.lv + (size_t)(v1 < a.N ? v1 : 0) * a.Ppad);
+        uint32_t s0 = 0, s1 = 0;
+        for (int c = 0; c < nc; c++) {
+            const uint4 qq = __ldg(q + c), x0 = __ldg(f0 + c), x1 = __ldg(f1 + c);
+            s0 = nvb_sad4(qq.x, x0.x, s0); s0 = nvb_sad4(qq.y, x0.y, s0);
+            s0 = nvb_sad4(qq.z, x0.z, s0); s0 = nvb_sad4(qq.w, x0.w, s0);
+            s1 = nvb_sad4(qq.x, x1.x, s1); s1 = nvb_sad4(qq.y, x1.y, s1);
+            s1 = nvb_sad4(qq.z, x1.z, s1); s1 = nvb_sad4(qq.w, x1.w, s1);
+        }
+        if (v0 < a.N && s0 <= thr)
+            atomicMin(a.exact + g, (unsigned long long)__double_as_longlong(
+                                       nvb_exact_diff_rows(a, qo, (size_t)v0 * a.Ppad, div255)));
+        if (v1 < a.N && s1 <= thr)
+            atomicMin(a.exact + g, (unsigned long long)__double_as_longlong(
+                                       nvb_exact_diff_rows(a, qo, (size_t)v1 * a.Ppad, div255)));
+    } else {
+        for (int v = v0; v < a.N && v <= v1; v += NVB_STEP_THREADS)
+            if (nvb_pair_score(a, qo, (size_t)v * a.Ppad) <= thr)
+                atomicMin(a.exact + g, (unsigned long long)__double_as_longlong(
+                                           nvb_exact_diff_rows(a, qo, (size_t)v * a.Ppad, div255)));
+    }
+}
+
+// claims and scans chunks of item `slot` until none is left or `budget` chunks are done;
+// returns the number of chunks scanned
+__device__ __forceinline__ int nvb_tie_sweep(const StepArgs &a, int slot, int n_chunks, int budget,
+                                             const double *div255)
+{
+    __shared__ int s_chunk;
+    const int g = a.tie_items[slot].x;
+    const unsigned long long thr = a.tie_thr[slot];
+    int done = 0;
+    while (done < budget) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_chunk = atomicAdd(a.tie_next + slot, 1);
+        __syncthreads();
+        const int c = s_chunk;
+        if (c >= n_chunks) break;
+        nvb_tie_scan_chunk(a, g, thr, c, div255);
+        done++;
+    }
+    return done;
+}
+
+__global__ void __launch_bounds__(NVB_STEP_THREADS, 8)
+k3_decide_help(StepArgs a)
+{
+    __shared__ double s_div[256];
+    __shared__ int s_slot0, s_nslots, s_count, s_go;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int epoch = *a.step_counter + 1;
+    const int n_chunks = (a.N + NVB_HELP_CHUNK - 1) / NVB_HELP_CHUNK;
+    for (int k = tid; k < 256; k += blockDim.x) s_div[k] = a.div255[k];
+    if (tid == 0) { s_slot0 = 0; s_nslots = 0; }
+    nvb_commit_pending(a, b);
+    const bool active = nvb_agent_active(a.ag, b);
+    if (tid == 0) a.ag.stepped[b] = active ? 1 : 0;
+    if (active) {
+        // --- decide (as nvb_decide<false>, with the tied headings of this agent in one
+        //     contiguous run of queue slots)
+        __shared__ unsigned long long s_min;
+        __shared__ int s_ntied;
+        const unsigned long long idx_mask = (1ull << a.idx_bits) - 1ull;
+        if (tid == 0) { s_min = ~0ull; s_ntied = 0; }
+        __syncthreads();
+        unsigned long long local = ~0ull;
+        for (int k = tid; k < a.A; k += blockDim.x)
+            local = min(local, a.keys[(size_t)b * a.A + k] >> a.idx_bits);
+        if (local != ~0ull) atomicMin(&s_min, local);
+        __syncthreads();
+        const unsigned long long thr = s_min + a.band;
+        for (int k = tid; k < a.A; k += blockDim.x)
+            if ((a.keys[(size_t)b * a.A + k] >> a.idx_bits) <= thr) atomicAdd(&s_ntied, 1);
+        __syncthreads();
+        const bool have_ties = s_ntied > 1;
+        __syncthreads();   // everyone has read s_ntied before it is reused
+        if (have_ties && tid == 0) {
+            s_nslots = s_ntied;
+            s_slot0 = atomicAdd(a.tie_count, s_ntied);
+            s_ntied = 0;   // reused as the running slot offset below
+        }
+        __syncthreads();
+        for (int k = tid; k < a.A; k += blockDim.x) {
+            const size_t g = (size_t)b * a.A + k;
+            const unsigned long long key = a.keys[g];
+            const bool tied = have_ties && (key >> a.idx_bits) <= thr;
+            unsigned long long ebits = NVB_EXACT_NONE;
+            if (!tied) {   // the tie scan revisits the best view of a tied heading anyway
+                const long long v = (long long)(key & idx_mask) - a.view_offset;
+                if (key != NVB_KEY_NONE && v >= 0 && v < a.N)
+                    ebits = (unsigned long long)__double_as_longlong(
+                        nvb_exact_diff_rows(a, g * a.Ppad, (size_t)v * a.Ppad, s_div));
+            }
+            a.exact[g] = ebits;
+            if (tied) {
+                const int slot = s_slot0 + atomicAdd(&s_ntied, 1);
+                a.tie_items[slot] = make_int2((int)g, 0);
+                a.tie_thr[slot] = thr;
+                a.tie_next[slot] = 0;
+                __threadfence();
+                *(volatile int *)(a.tie_ready + slot) = epoch;   // published
+            }
+        }
+        __syncthreads();
+        // --- the owner sweeps its own items to the end
+        for (int i = 0; i < s_nslots; i++) nvb_tie_sweep(a, s_slot0 + i, n_chunks, 1 << 30, s_div);
+    }
+    // --- everybody helps once with what is published by now: one parallel look at the
+    //     queue (a thread per slot), then at most NVB_HELP_BUDGET chunks, starting at a
+    //     CTA-dependent item so that the helpers spread over the queue
+    __shared__ int s_list[NVB_STEP_THREADS];
+    __syncthreads();
+    if (tid == 0) { s_count = *(volatile int *)a.tie_count; s_go = 0; }
+    __syncthreads();
+    const int count = min(s_count, NVB_STEP_THREADS);
+    if (count == 0) return;
+    if (tid < count && !(tid >= s_slot0 && tid < s_slot0 + s_nslots) &&
+        *(volatile int *)(a.tie_ready + tid) == epoch && *(volatile int *)(a.tie_next + tid) < n_chunks)
+        s_list[atomicAdd(&s_go, 1)] = tid;
+    __syncthreads();
+    const int n_list = s_go;
+    if (n_list == 0) return;
+    __threadfence();
+    // at most NVB_HELP_BUDGET chunks and NVB_HELP_BUDGET + 1 claim attempts: an item that
+    // looked unfinished may have been drained by others in the meantime
+    int budget = NVB_HELP_BUDGET;
+    for (int i = 0; i < n_list && i <= NVB_HELP_BUDGET && budget > 0; i++)
+        budget -= nvb_tie_sweep(a, s_list[(i + b) % n_list], n_chunks, budget, s_div);
+}
+
+template <bool NEED_HS, int PH, int PW>
+__global__ void __launch_bounds__(NVB_STEP_THREADS, 8)
+k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs sa)
+{
+    extern __shared__ __align__(128) uint8_t smem_k3ms[];
+    const int b = blockIdx.x;
+    if (!a.ag.stepped[b]) {
+        nvb_log_idle(a, b);
+        return;
+    }
+    double pose[3];
+    const bool more = nvb_move(a, b, nullptr, pose);
+    if (!more) return;
+    __syncthreads();
+    nvb_sample_body<NEED_HS, PH, PW>(&tmap, sa, b, pose[0], pose[1], pose[2], smem_k3ms, a.pending_fail + b);
 }
 
 // ---- three launches (large / view-sharded libraries) -----------------------------
 __global__ void __launch_bounds__(NVB_STEP_THREADS)
 k3_decide(StepArgs a)
 {
-    __shared__ double s_div[256];
     const int b = blockIdx.x;
+    nvb_commit_pending(a, b);
     const bool active = nvb_agent_active(a.ag, b);
     if (threadIdx.x == 0) a.ag.stepped[b] = active ? 1 : 0;
     if (!active) return;
-    nvb_load_div255(a, s_div);
-    nvb_decide<false>(a, b, s_div);
+    nvb_decide<false>(a, b, nullptr, a.div255);
 }
 
 // Tie pass: every (tied glimpse, local view) pair whose score is within the
@@ -352,5 +678,6 @@ k3_move(StepArgs a)
         nvb_log_idle(a, b);
         return;
     }
-    nvb_move(a, b);
+    double pose[3];
+    nvb_move(a, b, nullptr, pose);
 }

@@ -51,6 +51,7 @@ SIGNATURES = {
     "nvb_agents_steps_done": (_i, [_vp]),
     "nvb_agents_phase": (_i, [_vp, _i, _i, _i]),
     "nvb_device_ptr": (_vp, [_vp, _i]),
+    "nvb_debug_step_clocks": (_i, [_vp, _vp]),
     "nvb_launch_count": (_i64, [_vp]),
     "nvb_probe_sad_peak": (_d, [_vp, _i]),
     "nvb_time_distance_kernel": (_d, [_vp, _i]),
