@@ -276,6 +276,13 @@ def run_ours(args):
         "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
         "traffic": None,
     }
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "k2_traffic.json")) as f:
+            tr = json.load(f)
+        roofline["traffic"] = tr["dram_bytes_per_launch"]
+        roofline["traffic_source"] = tr["source"]
+    except Exception:
+        pass
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
