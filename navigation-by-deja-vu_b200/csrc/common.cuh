@@ -56,6 +56,15 @@ __device__ __forceinline__ uint32_t nvb_sad4(uint32_t a, uint32_t b, uint32_t ac
 #define NVB_TWO_PI 6.283185307179586476925286766559
 #define NVB_PI 3.14159265358979323846
 
+// Programmatic dependent launch: blocks until the preceding kernel of the stream has
+// completed and its writes are visible (a no-op for a normally launched kernel).  The
+// kernels of the step sequence are launched with programmatic stream serialization,
+// so their launch latency and prologue overlap the tail of the previous kernel.
+__device__ __forceinline__ void nvb_grid_dep_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---- mbarrier / TMA helpers (inline PTX; sm_100a) -------------------------
 __device__ __forceinline__ uint32_t nvb_smem_u32(const void *p)
 {

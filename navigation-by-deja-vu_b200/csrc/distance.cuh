@@ -100,6 +100,15 @@ k2_sad_v(DistArgs a)
 
     const int tid = threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;
+    if (BULK) {
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; s++) nvb_mbar_init(full + s, 1);
+            nvb_fence_barrier_init();
+        }
+        __syncthreads();
+    }
+    nvb_grid_dep_wait();   // everything above overlaps the previous kernel's tail
     if (a.step_counter != nullptr && blockIdx.x == 0 && tid == 0) {
         // one step-batch = one launch of this kernel: next log slot, empty tie list
         // (the kernels that read them run after this one)
@@ -110,15 +119,6 @@ k2_sad_v(DistArgs a)
     const int nk = BULK ? 1 : a.nk;
     const int total = (u1 - u0) * nk;
     if (total <= 0) return;
-
-    if (BULK) {
-        if (tid == 0) {
-#pragma unroll
-            for (int s = 0; s < STAGES; s++) nvb_mbar_init(full + s, 1);
-            nvb_fence_barrier_init();
-        }
-        __syncthreads();
-    }
 
     // (gt, vt, kc) of the next job to LOAD, advanced incrementally (no divisions in the loop)
     int l_gt = u0 / a.n_vt, l_vt = u0 - l_gt * a.n_vt, l_kc = 0, l_it = 0;
@@ -305,6 +305,7 @@ k2_sad_hsv(DistArgs a)
     uint8_t *smem = smem_hsv;
     const int g0 = blockIdx.x * NVB_HSV_TG;
     const int tid = threadIdx.x;
+    nvb_grid_dep_wait();
     if (a.step_counter != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
         *a.step_counter += 1;
         *a.tie_count = 0;

@@ -108,11 +108,51 @@ struct nvb_engine {
     size_t ev_used = 0;
     double k2_ms = 0.0;
     long long k2_count = 0;
+    std::vector<cudaEvent_t> ev3;   // tuning aid: decide / ties / move+sample
+    size_t ev3_used = 0;
     // log
     int log_cap = 0, log_A = 0;
     int16_t *log_best = nullptr;
     double *log_pose = nullptr, *log_sfam = nullptr, *log_afam = nullptr;
 };
+
+// Step form for small un-sharded libraries, NAVSIM_B200_STEP_FORM (measured warm on C2):
+//   3 (default)  K2 | decide | grid-wide tie pass | move + sample      62 us / step-batch
+//   1            K2 | decide + ties + move + sample in one launch      69 us (tie agents set the tail)
+//   2            K2 | decide + cooperative ties | move + sample        78 us
+static int step_form()
+{
+    static const int v = getenv("NAVSIM_B200_STEP_FORM") ? atoi(getenv("NAVSIM_B200_STEP_FORM")) : 3;
+    return (v >= 1 && v <= 3) ? v : 3;
+}
+
+static bool split_step() { return step_form() != 1; }
+
+// Launch with programmatic stream serialization (PDL): the kernel may start while the
+// previous kernel of the stream drains; every kernel of the step sequence begins
+// with griddepcontrol.wait before it touches global memory.
+static bool use_pdl()
+{
+    static const bool v = getenv("NAVSIM_B200_NO_PDL") == nullptr;
+    return v;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_seq(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = use_pdl() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // ---------------------------------------------------------------------------
 static void free_dev(void *p)
@@ -446,7 +486,7 @@ static int launch_dist_cfg2(nvb_engine *e, DistArgs da)
     da.n_vt = n_vt;
     da.vt_per_split = 0;
     da.spans = e->d_spans;
-    kern<<<(unsigned)n_cta, NVB_DIST_THREADS, C::SMEM, e->stream>>>(da);
+    CK(launch_seq(kern, dim3((unsigned)n_cta), dim3(NVB_DIST_THREADS), C::SMEM, e->stream, da));
     e->launches++;
     CK(cudaGetLastError());
     return NVB_OK;
@@ -972,7 +1012,7 @@ static int launch_k31_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa,
         CK(cudaFuncSetAttribute(k31_step_sample<HS, PH, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
     }
-    k31_step_sample<HS, PH, PW><<<e->B, NVB_STEP_THREADS, smem, e->stream>>>(e->tmap, s, sa);
+    CK(launch_seq(k31_step_sample<HS, PH, PW>, dim3(e->B), dim3(NVB_STEP_THREADS), smem, e->stream, e->tmap, s, sa));
     e->launches++;
     CK(cudaGetLastError());
     return NVB_OK;
@@ -987,8 +1027,27 @@ static int launch_k3ms_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa
         CK(cudaFuncSetAttribute(k3_move_sample<HS, PH, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
     }
-    k3_decide_help<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
-    k3_move_sample<HS, PH, PW><<<e->B, NVB_STEP_THREADS, smem, e->stream>>>(e->tmap, s, sa);
+    const bool three = step_form() == 3;
+    cudaEvent_t *tev = nullptr;
+    if (e->timing && getenv("NAVSIM_B200_TIME_ALL")) {   // tuning aid: events around every kernel
+        if (e->ev3.size() < e->ev3_used + 4) {
+            for (int i = 0; i < 256; i++) { cudaEvent_t ev; cudaEventCreate(&ev); e->ev3.push_back(ev); }
+        }
+        tev = &e->ev3[e->ev3_used];
+        e->ev3_used += 4;
+        cudaEventRecord(tev[0], e->stream);
+    }
+    if (three) {   // decide | grid-wide tie pass | move + sample
+        CK(launch_seq(k3_decide, dim3(e->B), dim3(NVB_STEP_THREADS), 0, e->stream, s));
+        if (tev) cudaEventRecord(tev[1], e->stream);
+        CK(launch_seq(k3_ties, dim3(e->sm_count * 2), dim3(NVB_TIE_THREADS), 0, e->stream, s));
+        if (tev) cudaEventRecord(tev[2], e->stream);
+        e->launches += 1;
+    } else {
+        k3_decide_help<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
+    }
+    CK(launch_seq(k3_move_sample<HS, PH, PW>, dim3(e->B), dim3(NVB_STEP_THREADS), smem, e->stream, e->tmap, s, sa));
+    if (tev) cudaEventRecord(tev[3], e->stream);
     e->launches += 2;
     CK(cudaGetLastError());
     return NVB_OK;
@@ -1067,12 +1126,6 @@ static int launch_distance_timed(nvb_engine *e, int G)
 // scans the library for its own tied headings); otherwise the three-launch form
 // with the grid-wide tie pass.
 #define NVB_FUSED_STEP_MAX_VIEWS 65536
-
-static bool split_step()
-{
-    static const bool v = getenv("NAVSIM_B200_SPLIT_STEP") != nullptr;
-    return v;
-}
 
 static bool fused_step(const nvb_engine *e)
 {
@@ -1158,7 +1211,7 @@ static int run_steps(nvb_engine *e, int nsteps, int fake, int log_afam, bool eag
             if ((rc = launch_sampler(e, agent_sampler_args(e), e->B))) return rc;
             e->glimpses_pending = true;
         }
-        const int per_step = fused_step(e) ? (split_step() ? 3 : 2) : 5;   // K2, step+sample | K1, K2, decide, ties, move
+        const int per_step = fused_step(e) ? (step_form() == 3 ? 4 : step_form() == 2 ? 3 : 2) : 5;   // K2, step+sample | K1, K2, decide, ties, move
         for (int i = done; i < nsteps; i++) {
             CK(cudaGraphLaunch(e->graph_exec, e->stream));
             e->launches += per_step;
@@ -1251,6 +1304,18 @@ extern "C" double nvb_kernel_time_ms(nvb_engine *e, int64_t *count)
         }
     }
     e->ev_used = 0;
+    if (e->ev3_used) {
+        double t[3] = {0, 0, 0};
+        for (size_t i = 0; i + 3 < e->ev3_used + 1 && i + 3 < e->ev3.size(); i += 4)
+            for (int k = 0; k < 3; k++) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, e->ev3[i + k], e->ev3[i + k + 1]) == cudaSuccess) t[k] += ms;
+            }
+        const double n = (double)(e->ev3_used / 4);
+        fprintf(stderr, "[navsim_b200] per step: K2 %.2f us, decide %.2f us, ties %.2f us, move+sample %.2f us\n",
+                e->k2_count ? e->k2_ms / e->k2_count * 1e3 : 0.0, t[0] / n * 1e3, t[1] / n * 1e3, t[2] / n * 1e3);
+        e->ev3_used = 0;
+    }
     if (count) *count = e->k2_count;
     return e->k2_ms;
 }

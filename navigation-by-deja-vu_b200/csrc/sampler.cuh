@@ -314,6 +314,7 @@ template <bool NEED_HS, int PH, int PW>
 __global__ void __launch_bounds__(NVB_SAMPLER_THREADS)
 k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
 {
+    nvb_grid_dep_wait();
     extern __shared__ __align__(128) uint8_t smem_k1[];
     const int b = blockIdx.x;
     if (a.agent_mode) {

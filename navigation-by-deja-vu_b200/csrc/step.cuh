@@ -422,6 +422,7 @@ __device__ __forceinline__ void nvb_commit_pending(const StepArgs &a, int b)
 __global__ void __launch_bounds__(NVB_STEP_THREADS, 8)
 k3_step(StepArgs a)
 {
+    nvb_grid_dep_wait();
     __shared__ unsigned long long s_exact[NVB_STEP_MAX_A_SMEM];
     __shared__ double s_div[256];
     const int b = blockIdx.x;
@@ -444,6 +445,7 @@ template <bool NEED_HS, int PH, int PW>
 __global__ void __launch_bounds__(NVB_STEP_THREADS, 8)   // 1024 agents = 7 CTAs per SM: one wave
 k31_step_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs sa)
 {
+    nvb_grid_dep_wait();
     extern __shared__ __align__(128) uint8_t smem_k31[];
     __shared__ unsigned long long s_exact[NVB_STEP_MAX_A_SMEM];
     __shared__ double s_div[256];
@@ -534,6 +536,7 @@ __device__ __forceinline__ int nvb_tie_sweep(const StepArgs &a, int slot, int n_
 __global__ void __launch_bounds__(NVB_STEP_THREADS, 8)
 k3_decide_help(StepArgs a)
 {
+    nvb_grid_dep_wait();
     __shared__ double s_div[256];
     __shared__ int s_slot0, s_nslots, s_count, s_go;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -621,6 +624,7 @@ template <bool NEED_HS, int PH, int PW>
 __global__ void __launch_bounds__(NVB_STEP_THREADS, 8)
 k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs sa)
 {
+    nvb_grid_dep_wait();
     extern __shared__ __align__(128) uint8_t smem_k3ms[];
     const int b = blockIdx.x;
     if (!a.ag.stepped[b]) {
@@ -638,6 +642,7 @@ k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs
 __global__ void __launch_bounds__(NVB_STEP_THREADS)
 k3_decide(StepArgs a)
 {
+    nvb_grid_dep_wait();
     const int b = blockIdx.x;
     nvb_commit_pending(a, b);
     const bool active = nvb_agent_active(a.ag, b);
@@ -652,6 +657,7 @@ k3_decide(StepArgs a)
 __global__ void __launch_bounds__(NVB_TIE_THREADS)
 k3_ties(StepArgs a)
 {
+    nvb_grid_dep_wait();
     const int n_items = *a.tie_count;
     if (n_items == 0) return;
     const int chunks = (a.N + NVB_TIE_THREADS - 1) / NVB_TIE_THREADS;
@@ -673,6 +679,7 @@ k3_ties(StepArgs a)
 __global__ void __launch_bounds__(NVB_STEP_THREADS)
 k3_move(StepArgs a)
 {
+    nvb_grid_dep_wait();
     const int b = blockIdx.x;
     if (!a.ag.stepped[b]) {
         nvb_log_idle(a, b);
