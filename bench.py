@@ -156,9 +156,10 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
 
-    # ---- warm-up (also captures the step graph)
+    # ---- warm-up: W step-batches, and one full rewind period so that the step log has
+    # its final capacity and the step graph is captured before anything is timed
     eng.rewind()
-    eng.step(W)
+    eng.step(max(W, rewind_every))
     eng.sync()
 
     # ---- value: K step-batches, device resident, cold L2 per step, CUDA events

@@ -98,6 +98,9 @@ struct nvb_engine {
     int32_t *d_budget0 = nullptr;
     // CUDA graph of one step-batch (phase1+2+3), keyed on (fake, log_afam, log buffers)
     cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphExec_t graph_io = nullptr;   // one step-batch from fresh poses, nothing sampled ahead
+    const void *graph_io_log_ptr = nullptr;
+    int graph_io_log_cap = -1;
     int graph_fake = -1, graph_afam = -1, graph_log_cap = -1, graph_B = -1;
     const void *graph_log_ptr = nullptr;
     bool graph_dirty = true;   // set by every call that changes what the captured kernels were given
@@ -299,6 +302,7 @@ extern "C" void nvb_engine_destroy(nvb_engine *e)
                     e->ag.stepped, e->d_step, e->log_best, e->log_pose, e->log_sfam, e->log_afam,
                     e->d_poses0, e->d_budget0, e->d_spans, e->d_pending};
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->graph_io) cudaGraphExecDestroy(e->graph_io);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     for (void *p : ptrs) free_dev(p);
     if (e->own_stream) cudaStreamDestroy(e->stream);
@@ -1149,6 +1153,13 @@ static int one_step(nvb_engine *e, const StepArgs &s, bool sample_next = true)
             e->glimpses_pending = true;
             return NVB_OK;
         }
+        if (step_form() == 3) {   // decide | grid-wide tie pass | move, nothing sampled ahead
+            CK(launch_seq(k3_decide, dim3(e->B), dim3(NVB_STEP_THREADS), 0, e->stream, s));
+            CK(launch_seq(k3_ties, dim3(e->sm_count * 2), dim3(NVB_TIE_THREADS), 0, e->stream, s));
+            CK(launch_seq(k3_move, dim3(e->B), dim3(NVB_STEP_THREADS), 0, e->stream, s));
+            e->launches += 3;
+            return NVB_OK;
+        }
         k3_step<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
         e->launches++;
         CK(cudaGetLastError());
@@ -1170,6 +1181,7 @@ static int ensure_graph(nvb_engine *e, int fake, int log_afam)
 {
     if (graph_valid(e, fake, log_afam)) return NVB_OK;
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    if (e->graph_io) { cudaGraphExecDestroy(e->graph_io); e->graph_io = nullptr; }   // shares graph_dirty
     const StepArgs s = make_step_args(e, fake, log_afam);
     // warm every kernel's lazy attribute setup outside the capture
     const int64_t before = e->launches;
@@ -1268,7 +1280,40 @@ extern "C" int nvb_agents_step_io(nvb_engine *e, const double *poses_in, int nst
         CK(cudaMemsetAsync(e->d_pending, 0, sizeof(int32_t) * B, e->stream));
         e->glimpses_pending = false;   // sampled for the old poses
     }
-    if ((rc = run_steps(e, nsteps, 0, 0, poses_in != nullptr))) return rc;
+    if (poses_in != nullptr && nsteps == 1 && e->use_graph && !e->timing) {
+        // host-driven per-call form: the five launches of one step-batch replayed as a graph
+        if ((rc = ensure_log(e, e->steps_done + 1, false))) return rc;
+        const bool valid = e->graph_io && !e->graph_dirty && e->graph_io_log_ptr == e->log_best &&
+                           e->graph_io_log_cap == e->log_cap;
+        if (!valid) {
+            const StepArgs s = make_step_args(e, 0, 0);
+            if ((rc = one_step(e, s, false))) return rc;   // plain launches first: lazy attribute setup
+            e->steps_done += 1;
+            if (e->graph_io) { cudaGraphExecDestroy(e->graph_io); e->graph_io = nullptr; }
+            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+            const int64_t before = e->launches;
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+            e->glimpses_pending = false;
+            rc = one_step(e, s, false);
+            cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+            e->launches = before;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(NVB_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&e->graph_io, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(NVB_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+            e->graph_io_log_ptr = e->log_best;
+            e->graph_io_log_cap = e->log_cap;
+            e->graph_dirty = false;
+        } else {
+            CK(cudaGraphLaunch(e->graph_io, e->stream));
+            e->launches += fused_step(e) && step_form() != 3 ? 3 : 5;
+            e->steps_done += 1;
+        }
+    } else if ((rc = run_steps(e, nsteps, 0, 0, poses_in != nullptr))) {
+        return rc;
+    }
     const size_t t = (size_t)e->steps_done - 1;
     if (best_idx)
         CK(cudaMemcpyAsync(best_idx, e->log_best + t * B, sizeof(int16_t) * B, cudaMemcpyDeviceToHost, e->stream));
