@@ -85,6 +85,10 @@ __device__ __forceinline__ void nvb_mbar_expect_tx(uint64_t *bar, uint32_t bytes
                  "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void nvb_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nvb_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void nvb_mbar_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t done;

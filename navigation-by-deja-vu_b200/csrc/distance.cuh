@@ -73,7 +73,7 @@ struct DistCfg {
     static constexpr int TN = TX * MV;
     static constexpr int KC = 16 * CPR;
     static constexpr int STAGE_BYTES = (TG + TN) * KC;
-    static constexpr int SMEM = STAGE_BYTES * STAGES + 64;   // + mbarriers
+    static constexpr int SMEM = STAGE_BYTES * STAGES + 128;  // + full / empty mbarriers
 };
 
 // Work decomposition: a "unit" is one TG x TN (glimpse tile x view tile) block,
@@ -97,13 +97,17 @@ k2_sad_v(DistArgs a)
     extern __shared__ __align__(1024) uint8_t smem_k2[];
     uint8_t *smem = smem_k2;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGE_BYTES * STAGES);
+    uint64_t *empty = full + STAGES;   // BULK: one arrival per warp when a stage has been consumed
 
     const int tid = threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;
     if (BULK) {
         if (tid == 0) {
 #pragma unroll
-            for (int s = 0; s < STAGES; s++) nvb_mbar_init(full + s, 1);
+            for (int s = 0; s < STAGES; s++) {
+                nvb_mbar_init(full + s, 1);
+                nvb_mbar_init(empty + s, NVB_DIST_THREADS / 32);
+            }
             nvb_fence_barrier_init();
         }
         __syncthreads();
@@ -169,7 +173,7 @@ k2_sad_v(DistArgs a)
     uint32_t best[MG];     // smallest sum so far
     uint32_t best_at[MG];  // (view tile << 4) | j of the first view that reached it
 #pragma unroll
-    for (int i = 0; i < MG; i++) { best[i] = 0x0FFFFFFFu; best_at[i] = 0; }
+    for (int i = 0; i < MG; i++) { best[i] = 0x0EFFFFFFu; best_at[i] = 0; }
 
     int goff[MG], gsw[MG], voff[MV], vsw[MV];
 #pragma unroll
@@ -187,11 +191,20 @@ k2_sad_v(DistArgs a)
     int gt = u0 / a.n_vt, vt = u0 - gt * a.n_vt, kc = 0;   // job being computed
 
     for (int it = 0; it < total; it++) {
-        if (!BULK) nvb_cp_async_wait<STAGES - 2>();
-        __syncthreads();   // everyone is done with job it-1: its slot may be refilled
-        if (l_it < total) load_next();
-        if (!BULK) nvb_cp_async_commit();
-        if (BULK) nvb_mbar_wait(full + (it % STAGES), (uint32_t)((it / STAGES) & 1));
+        if (BULK) {
+            // no CTA-wide barrier: the loading thread alone waits until every warp has released
+            // the slot of job it-1, refills it, and each warp runs ahead as far as data has landed
+            if (tid == 0 && l_it < total) {
+                if (it > 0) nvb_mbar_wait(empty + ((it - 1) % STAGES), (uint32_t)(((it - 1) / STAGES) & 1));
+                load_next();
+            }
+            nvb_mbar_wait(full + (it % STAGES), (uint32_t)((it / STAGES) & 1));
+        } else {
+            nvb_cp_async_wait<STAGES - 2>();
+            __syncthreads();   // everyone is done with job it-1: its slot may be refilled
+            if (l_it < total) load_next();
+            nvb_cp_async_commit();
+        }
 
         const uint8_t *st = smem + (it % STAGES) * C::STAGE_BYTES;
 #pragma unroll(CPR <= 5 ? CPR : 1)
@@ -215,6 +228,10 @@ k2_sad_v(DistArgs a)
             }
         }
 
+        if (BULK) {
+            __syncwarp();
+            if ((tid & 31) == 0) nvb_mbar_arrive(empty + (it % STAGES));   // this warp is done with the slot
+        }
         if (++kc == nk) {
             kc = 0;
             // unit finished: fold its MG x MV sums into the per-thread running minimum.
@@ -225,23 +242,25 @@ k2_sad_v(DistArgs a)
                 for (int j = 0; j < MV; j++)
                     if (tx + TX * j >= nvalid) {
 #pragma unroll
-                        for (int i = 0; i < MG; i++) acc[i][j] = 0x0FFFFFFFu;   // > any real sum, * 16 fits
+                        for (int i = 0; i < MG; i++) acc[i][j] = 0x0EFFFFFFu;   // > any real sum, * 17 + 16 still fits in 32 bits
                     }
             }
 #pragma unroll
             for (int i = 0; i < MG; i++) {
-                // key = sum * 16 + j: the multiply-add runs on the FMA pipe, the 3-input
-                // minimum on the ALU pipe; the smallest key is the smallest sum and, among
-                // equal sums, the lowest view of this thread
-                uint32_t m = acc[i][0] * 16u;
+                // key = sum * 17 + j (j < 17): a true multiply-add, which runs on the FMA pipe
+                // (a power-of-two scale would become a shift-add on the busy ALU pipe); the
+                // 3-input minimum is the only ALU-pipe work per pair.  The smallest key is the
+                // smallest sum and, among equal sums, the lowest view of this thread.
+                uint32_t m = acc[i][0] * 17u;
 #pragma unroll
                 for (int j = 1; j + 1 < MV; j += 2)
-                    m = __vimin3_u32(m, acc[i][j] * 16u + (uint32_t)j, acc[i][j + 1] * 16u + (uint32_t)(j + 1));
-                if ((MV & 1) == 0) m = min(m, acc[i][MV - 1] * 16u + (uint32_t)(MV - 1));
+                    m = __vimin3_u32(m, acc[i][j] * 17u + (uint32_t)j, acc[i][j + 1] * 17u + (uint32_t)(j + 1));
+                if ((MV & 1) == 0) m = min(m, acc[i][MV - 1] * 17u + (uint32_t)(MV - 1));
                 // strict < on the sum alone: an equal sum in a later tile has a higher view index
-                if ((m >> 4) < best[i]) {
-                    best[i] = m >> 4;
-                    best_at[i] = ((uint32_t)vt << 4) | (m & 15u);
+                if (m < best[i] * 17u) {
+                    const uint32_t sum = m / 17u;
+                    best[i] = sum;
+                    best_at[i] = ((uint32_t)vt << 4) | (m - sum * 17u);
                 }
 #pragma unroll
                 for (int j = 0; j < MV; j++) acc[i][j] = 0;
@@ -251,7 +270,7 @@ k2_sad_v(DistArgs a)
 #pragma unroll
                 for (int i = 0; i < MG; i++) {
                     unsigned long long key = NVB_KEY_NONE;
-                    if (best[i] != 0x0FFFFFFFu) {
+                    if (best[i] != 0x0EFFFFFFu) {
                         const unsigned long long v = (unsigned long long)(
                             a.view_offset + (long long)(best_at[i] >> 4) * TN + tx + TX * (int)(best_at[i] & 15u));
                         key = ((unsigned long long)best[i] << a.idx_bits) | v;
@@ -263,7 +282,7 @@ k2_sad_v(DistArgs a)
                     }
                     const int g = gt * TG + ty + TY * i;
                     if ((tx % RW) == 0 && g < a.G && key != NVB_KEY_NONE) atomicMin(a.keys + g, key);
-                    best[i] = 0x0FFFFFFFu;
+                    best[i] = 0x0EFFFFFFu;
                     best_at[i] = 0;
                 }
             }

@@ -513,6 +513,11 @@ static int launch_dist_cpr(nvb_engine *e, const DistArgs &da)
     // many glimpses: 64-glimpse x 240- or 256-view tiles (4 x 15|16 sums per thread);
     // the width that wastes fewer padded views wins
     const long long pad15 = ((da.N + 239) / 240) * 240LL, pad16 = ((da.N + 255) / 256) * 256LL;
+    static const int mg = getenv("NAVSIM_B200_K2_MG") ? atoi(getenv("NAVSIM_B200_K2_MG")) : 4;
+    if (mg == 3) {   // tuning knob: 48-glimpse tiles (finer SM-level balance)
+        if (pad15 < pad16) return launch_dist_cfg<16, 3, 15, CPR>(e, da);
+        return launch_dist_cfg<16, 3, 16, CPR>(e, da);
+    }
     if (pad15 < pad16) return launch_dist_cfg<16, 4, 15, CPR>(e, da);
     return launch_dist_cfg<16, 4, 16, CPR>(e, da);
 }

@@ -274,7 +274,10 @@ __device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const S
             }
             done = worst < c.tie;
         }
-        if (!done) sum_v = nvb_block_careful<NEED_HS>(c, cf, sf, col0, row0, hh, ss, &n, &err);
+        if (!done) {
+            if (a.dbg) atomicAdd((unsigned long long *)a.dbg + b * 8 + 7, 1ull);
+            sum_v = nvb_block_careful<NEED_HS>(c, cf, sf, col0, row0, hh, ss, &n, &err);
+        }
         // util.pyx:121-123: V = (uint8) round(sum / (fr*fc)), half away from zero.  In
         // integers: the quotient is either an exact tie or at least 1/(2*fr*fc) away
         // from one, far more than the FP64 division's rounding.

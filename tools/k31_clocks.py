@@ -28,4 +28,5 @@ for i in order:
 hist, edges = np.histogram(tot, bins=[0, 10, 15, 20, 25, 30, 40, 60])
 print("total-duration histogram:", dict(zip(["<10", "<15", "<20", "<25", "<30", "<40", "<60"], hist)))
 
+print("careful-path blocks per agent (of %d): mean %.2f max %d" % (800, d[:, 7].mean(), d[:, 7].max()))
 print("agents with tie scans:", int((d[:, 7] > 0).sum()), " exact evaluations: mean %.1f max %d" % (d[d[:, 7] > 0, 7].mean(), d[:, 7].max()))
