@@ -179,6 +179,19 @@ int nvb_agents_steps_done(nvb_engine *e);
  * phase 3 moves the agents.  nvb_agents_step() runs the three back to back. */
 int nvb_agents_phase(nvb_engine *e, int phase, int fake, int log_afam);
 
+/* View shards over NVLink peer memory (no NCCL, no host round trip per step): with
+ * the exchange attached, nvb_agents_step() runs the sharded sequence itself --
+ * K1, K2, MIN exchange of the keys, decide, ties, MIN exchange of the exact
+ * differences, move -- where the exchange is a kernel that publishes into the
+ * peers' mapped memory, waits for their flags (bounded) and reduces with P2P loads.
+ * Order: nvb_library_set_shard, nvb_agents_set, nvb_p2p_export (64-byte CUDA IPC
+ * handle of this rank's exchange area), all-gather the handles out of band,
+ * nvb_p2p_attach(rank, world, handles [world][64]).  nvb_p2p_error() != 0 after a
+ * synchronisation means a peer did not arrive within ~2 s. */
+int nvb_p2p_export(nvb_engine *e, void *handle64);
+int nvb_p2p_attach(nvb_engine *e, int rank, int world, const void *handles64);
+int nvb_p2p_error(nvb_engine *e);
+
 #define NVB_PTR_KEYS 0 /* uint64 [B*A]  */
 #define NVB_PTR_TIE 1  /* uint64 [B*A]  (FP64 bit patterns) */
 #define NVB_PTR_POSES 2 /* double [B][3] */

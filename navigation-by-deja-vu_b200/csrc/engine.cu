@@ -91,6 +91,13 @@ struct nvb_engine {
     int steps_done = 0;
     int *d_spans = nullptr;         // per-CTA unit spans of the distance kernel
     int span_key[4] = {-1, -1, -1, -1};
+    // view-sharded library over NVLink peer memory
+    P2PArea *d_xarea = nullptr;
+    P2PArgs p2p{};
+    bool p2p_on = false;
+    unsigned long long *d_p2p_seq = nullptr;
+    int *d_p2p_err = nullptr;
+    void *p2p_opened[NVB_P2P_MAX_RANKS] = {nullptr};
     long long *d_dbg = nullptr;     // tuning aid: per-agent clock64 checkpoints of one step
     int32_t *d_pending = nullptr;   // [B] sampler failure parked for the next step (fused loop)
     bool glimpses_pending = false;  // the glimpses of the next step are already sampled
@@ -301,6 +308,9 @@ extern "C" void nvb_engine_destroy(nvb_engine *e)
                     e->ag.budget, e->ag.nav_frames, e->ag.err_sum, e->ag.err_n, e->ag.coverage,
                     e->ag.stepped, e->d_step, e->log_best, e->log_pose, e->log_sfam, e->log_afam,
                     e->d_poses0, e->d_budget0, e->d_spans, e->d_pending};
+    for (int i = 0; i < NVB_P2P_MAX_RANKS; i++)
+        if (e->p2p_opened[i]) cudaIpcCloseMemHandle(e->p2p_opened[i]);
+    free_dev(e->d_xarea); free_dev(e->d_p2p_seq); free_dev(e->d_p2p_err);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     if (e->graph_io) cudaGraphExecDestroy(e->graph_io);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
@@ -1089,8 +1099,18 @@ static int launch_k31(nvb_engine *e, const StepArgs &s)
     return launch_k31_t<false, 0, 0>(e, s, sa, smem);
 }
 
+static int p2p_exchange(nvb_engine *e, unsigned long long *values)
+{
+    if (!e->p2p_on) return NVB_OK;
+    CK(launch_seq(k_p2p_min, dim3(1), dim3(NVB_P2P_THREADS), 0, e->stream, e->p2p, values, e->B * e->A));
+    e->launches++;
+    return NVB_OK;
+}
+
 static int phase2(nvb_engine *e, const StepArgs &s)
 {
+    int xrc = p2p_exchange(e, e->d_keys);          // keys: MIN over ranks before anybody decides
+    if (xrc) return xrc;
     k3_decide<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
     k3_ties<<<e->sm_count * 4, NVB_TIE_THREADS, 0, e->stream>>>(s);
     e->launches += 2;
@@ -1100,6 +1120,8 @@ static int phase2(nvb_engine *e, const StepArgs &s)
 
 static int phase3(nvb_engine *e, const StepArgs &s)
 {
+    int xrc = p2p_exchange(e, e->d_exact);         // exact differences: MIN over ranks before the move
+    if (xrc) return xrc;
     k3_move<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
     e->launches++;
     CK(cudaGetLastError());
@@ -1466,6 +1488,65 @@ extern "C" int nvb_debug_step_clocks(nvb_engine *e, long long *out)
     e->d_dbg = nullptr;
     e->graph_dirty = true;
     return rc;
+}
+
+// ---- view shards over NVLink peer memory -----------------------------------------
+extern "C" int nvb_p2p_export(nvb_engine *e, void *handle64)
+{
+    if (e->B <= 0) return fail(NVB_E_INVALID, "set the agents before exporting the exchange area");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    const long long cap = (long long)e->B * e->A;
+    const size_t bytes = sizeof(P2PArea) + sizeof(unsigned long long) * (size_t)(2 * cap);
+    free_dev(e->d_xarea);
+    e->d_xarea = nullptr;
+    CK(cudaMalloc((void **)&e->d_xarea, bytes));
+    CK(cudaMemset(e->d_xarea, 0, bytes));
+    int rc;
+    if ((rc = alloc_dev(&e->d_p2p_seq, 1))) return rc;
+    if ((rc = alloc_dev(&e->d_p2p_err, 1))) return rc;
+    CK(cudaMemset(e->d_p2p_seq, 0, sizeof(unsigned long long)));
+    CK(cudaMemset(e->d_p2p_err, 0, sizeof(int)));
+    e->p2p.cap = cap;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, e->d_xarea));
+    return NVB_OK;
+}
+
+extern "C" int nvb_p2p_attach(nvb_engine *e, int rank, int world, const void *handles64)
+{
+    if (!e->d_xarea) return fail(NVB_E_INVALID, "call nvb_p2p_export first");
+    if (world < 2 || world > NVB_P2P_MAX_RANKS || rank < 0 || rank >= world)
+        return fail(NVB_E_INVALID, "bad rank/world");
+    CK(cudaSetDevice(e->device));
+    e->p2p.self = e->d_xarea;
+    e->p2p.rank = rank;
+    e->p2p.world = world;
+    e->p2p.seq = e->d_p2p_seq;
+    e->p2p.error = e->d_p2p_err;
+    e->p2p.spin_limit = 4000000000ll;   // ~2 s of SM clock: a peer that never shows up is an error, not a hang
+    for (int p = 0; p < world; p++) {
+        if (p == rank) { e->p2p.peer[p] = e->d_xarea; continue; }
+        void *ptr = nullptr;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles64 + 64 * p, 64);
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        e->p2p_opened[p] = ptr;
+        e->p2p.peer[p] = (P2PArea *)ptr;
+    }
+    e->p2p_on = true;
+    e->graph_dirty = true;
+    return NVB_OK;
+}
+
+extern "C" int nvb_p2p_error(nvb_engine *e)
+{
+    if (!e->d_p2p_err) return 0;
+    int v = 0;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    cudaMemcpy(&v, e->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost);
+    return v;
 }
 
 extern "C" double nvb_probe_sad_peak(nvb_engine *e, int iters)

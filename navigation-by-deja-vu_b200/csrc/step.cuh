@@ -688,3 +688,69 @@ k3_move(StepArgs a)
     double pose[3];
     nvb_move(a, b, nullptr, pose);
 }
+
+
+// ---- MIN exchange over NVLink peer memory (view-sharded library, one process per GPU) ----
+// Every rank owns an exchange area {flags[NVB_P2P_MAX_RANKS], data[2][cap]} that its peers
+// have mapped through CUDA IPC.  One exchange = publish my values (double buffered by the
+// exchange's parity), raise my flag in every peer's area (P2P store), wait until every
+// peer's flag for this exchange has arrived in MY area (local polling, bounded), then MIN
+// the peers' values into mine (P2P loads that bypass L1).  A rank can be at most one
+// exchange ahead of a peer -- it cannot pass the wait of exchange s+1 before that peer has
+// finished reading exchange s and published s+1 -- so two buffers suffice.  The sequence
+// number lives on the device and is bumped by the kernel, so the launch is graph-replayable
+// and a whole run of sharded steps is queued without any host round trip.
+#define NVB_P2P_MAX_RANKS 8
+#define NVB_P2P_THREADS 1024
+
+struct P2PArea {
+    unsigned long long flags[NVB_P2P_MAX_RANKS];
+    unsigned long long pad[8];
+    unsigned long long data[1];   // [2][cap]
+};
+
+struct P2PArgs {
+    P2PArea *self;
+    P2PArea *peer[NVB_P2P_MAX_RANKS];
+    int rank, world;
+    long long cap;
+    unsigned long long *seq;      // device: number of exchanges completed
+    int *error;                   // device: set to 1 if a peer did not show up in time
+    long long spin_limit;         // clock64 ticks
+};
+
+__global__ void __launch_bounds__(NVB_P2P_THREADS)
+k_p2p_min(P2PArgs x, unsigned long long *values, int n)
+{
+    nvb_grid_dep_wait();
+    const int tid = threadIdx.x;
+    const unsigned long long s = *x.seq;
+    unsigned long long *mine = x.self->data + (s & 1ull) * x.cap;
+    for (int i = tid; i < n; i += NVB_P2P_THREADS) mine[i] = values[i];
+    __threadfence_system();
+    __syncthreads();
+    if (tid < x.world && tid != x.rank) {
+        // raise my flag in the peer's area, then wait for the peer's flag in mine
+        volatile unsigned long long *theirs = x.peer[tid]->flags + x.rank;
+        *theirs = s + 1ull;
+        volatile unsigned long long *ours = x.self->flags + tid;
+        const long long t0 = clock64();
+        while (*ours < s + 1ull) {
+            if (clock64() - t0 > x.spin_limit) { *x.error = 1; break; }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += NVB_P2P_THREADS) {
+        unsigned long long m = values[i];
+        for (int p = 0; p < x.world; p++) {
+            if (p == x.rank) continue;
+            const unsigned long long v = __ldcv(x.peer[p]->data + (s & 1ull) * x.cap + i);
+            m = v < m ? v : m;
+        }
+        values[i] = m;
+    }
+    __syncthreads();
+    if (tid == 0) *x.seq = s + 1ull;
+}

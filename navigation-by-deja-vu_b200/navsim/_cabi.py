@@ -50,6 +50,9 @@ SIGNATURES = {
     "nvb_agents_log": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "nvb_agents_steps_done": (_i, [_vp]),
     "nvb_agents_phase": (_i, [_vp, _i, _i, _i]),
+    "nvb_p2p_export": (_i, [_vp, _vp]),
+    "nvb_p2p_attach": (_i, [_vp, _i, _i, _vp]),
+    "nvb_p2p_error": (_i, [_vp]),
     "nvb_device_ptr": (_vp, [_vp, _i]),
     "nvb_debug_step_clocks": (_i, [_vp, _vp]),
     "nvb_launch_count": (_i64, [_vp]),

@@ -179,6 +179,24 @@ class NavEngine(object):
         self.n_views = len(scenes)
         self._familiar_scenes = None
 
+    def p2p_attach(self, rank, world_size, group=None):
+        """View shards over NVLink peer memory: exchanges this rank's CUDA IPC handle with
+        its peers (torch.distributed, any backend) and attaches them.  Afterwards step()
+        runs the sharded sequence on the device without NCCL or host round trips.  Call
+        after set_library_shard() and set_agents(); every rank must then call step() with
+        the same arguments."""
+        import torch.distributed as dist
+        handle = (C.c_ubyte * 64)()
+        check(self._lib.nvb_p2p_export(self._h, C.cast(handle, C.c_void_p)))
+        gathered = [None] * world_size
+        dist.all_gather_object(gathered, bytes(handle), group=group)
+        blob = (C.c_ubyte * (64 * world_size)).from_buffer_copy(b"".join(gathered))
+        check(self._lib.nvb_p2p_attach(self._h, int(rank), int(world_size), C.cast(blob, C.c_void_p)))
+        dist.barrier(group=group)   # every rank has mapped every area before anybody steps
+
+    def p2p_error(self):
+        return int(self._lib.nvb_p2p_error(self._h))
+
     def _set_path_only(self, path):
         check(self._lib.nvb_set_training_path(self._h, ptr(path), len(path)))
 

@@ -51,9 +51,30 @@ def main():
         got = eng.log(0, frames)
         same = np.array_equal(got["best_idx"], want["best_idx"]) and np.array_equal(got["poses"], want["poses"])
         ok = ok and same
-        print("rank %d %-8s views [%d, %d) of %d: %s  (%.1f us/step incl. 2 NCCL all-reduces)" %
+        print("rank %d %-8s views [%d, %d) of %d: NCCL all-reduce  %s  (%.1f us/step, host-driven phases)" %
               (rank, name, off, off + cnt, len(scenes), "identical to unsharded" if same else "MISMATCH",
                dt / frames * 1e6), flush=True)
+        # the same shards, exchanged over NVLink peer memory inside the step sequence
+        eng2 = NavEngine(L, device=local, stream=stream.cuda_stream, **w)
+        eng2.set_library_shard(scenes[off:off + cnt], off, len(scenes), tpath)
+        eng2.set_agents(poses, frames)
+        eng2.p2p_attach(rank, world)
+        eng2.step(3)                      # warm-up: plain launches + graph capture
+        eng2.sync()
+        eng2.rewind()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng2.step(frames)
+        eng2.sync()
+        dt2 = time.perf_counter() - t0
+        got2 = eng2.log(0, frames)
+        same2 = (np.array_equal(got2["best_idx"], want["best_idx"]) and np.array_equal(got2["poses"], want["poses"])
+                 and eng2.p2p_error() == 0)
+        ok = ok and same2
+        print("rank %d %-8s views [%d, %d) of %d: NVLink P2P exchange %s  (%.1f us/step, device-resident)" %
+              (rank, name, off, off + cnt, len(scenes), "identical to unsharded" if same2 else "MISMATCH",
+               dt2 / frames * 1e6), flush=True)
     flag = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
