@@ -98,6 +98,7 @@ struct nvb_engine {
     unsigned long long *d_p2p_seq = nullptr;
     int *d_p2p_err = nullptr;
     void *p2p_opened[NVB_P2P_MAX_RANKS] = {nullptr};
+    unsigned long long *d_dmin2 = nullptr;   // [B] long-path form of update_error
     long long *d_dbg = nullptr;     // tuning aid: per-agent clock64 checkpoints of one step
     int32_t *d_pending = nullptr;   // [B] sampler failure parked for the next step (fused loop)
     bool glimpses_pending = false;  // the glimpses of the next step are already sampled
@@ -307,7 +308,7 @@ extern "C" void nvb_engine_destroy(nvb_engine *e)
                     e->d_tie_items, e->d_tie_thr, e->d_tie_next, e->d_tie_ready, e->ag.poses, e->ag.status, e->ag.completed,
                     e->ag.budget, e->ag.nav_frames, e->ag.err_sum, e->ag.err_n, e->ag.coverage,
                     e->ag.stepped, e->d_step, e->log_best, e->log_pose, e->log_sfam, e->log_afam,
-                    e->d_poses0, e->d_budget0, e->d_spans, e->d_pending};
+                    e->d_poses0, e->d_budget0, e->d_spans, e->d_pending, e->d_dmin2};
     for (int i = 0; i < NVB_P2P_MAX_RANKS; i++)
         if (e->p2p_opened[i]) cudaIpcCloseMemHandle(e->p2p_opened[i]);
     free_dev(e->d_xarea); free_dev(e->d_p2p_seq); free_dev(e->d_p2p_err);
@@ -480,7 +481,9 @@ static int build_spans(nvb_engine *e, int n_gt, int n_vt, int n_cta)
 template <int TY, int MG, int MV, int CPR, bool BULK>
 static int launch_dist_cfg2(nvb_engine *e, DistArgs da)
 {
-    constexpr int STAGES = 3;
+    // library streaming (one thread column per view, TY == 1): two stages so that two CTAs
+    // fit per SM; the big square tiles keep three
+    constexpr int STAGES = (TY == 1) ? 2 : (TY == 2) ? 4 : 3;
     using C = DistCfg<TY, MG, MV, CPR, STAGES>;
     auto kern = k2_sad_v<TY, MG, MV, CPR, STAGES, BULK>;
     static int occ_dev[64] = {0};
@@ -518,7 +521,10 @@ static int launch_dist_cfg(nvb_engine *e, const DistArgs &da)
 template <int CPR>
 static int launch_dist_cpr(nvb_engine *e, const DistArgs &da)
 {
-    if (da.G <= 16) return launch_dist_cfg<1, 16, 2, CPR>(e, da);      // 16 x 512 tiles: library streaming
+    // few glimpses (one agent's heading sweep): G x 512 tiles, the library streams through
+    // once; the row count is matched to the reference's default sweep of 10 headings
+    if (da.G <= 10) return launch_dist_cfg<2, 5, 2, CPR>(e, da);       // 10 x 256 tiles, 4 stages in flight
+    if (da.G <= 16) return launch_dist_cfg<1, 16, 2, CPR>(e, da);
     if (da.G <= 64) return launch_dist_cfg<4, 8, 4, CPR>(e, da);       // 32 x 256
     // many glimpses: 64-glimpse x 240- or 256-view tiles (4 x 15|16 sums per thread);
     // the width that wastes fewer padded views wins
@@ -932,6 +938,7 @@ extern "C" int nvb_agents_set(nvb_engine *e, const double *poses, const int32_t 
         if ((rc = alloc_dev(&e->d_poses0, (size_t)3 * B))) return rc;
         if ((rc = alloc_dev(&e->d_budget0, (size_t)B))) return rc;
         if ((rc = alloc_dev(&e->d_pending, (size_t)B))) return rc;
+        if ((rc = alloc_dev(&e->d_dmin2, (size_t)B))) return rc;
         free_dev(e->log_best); free_dev(e->log_pose); free_dev(e->log_sfam); free_dev(e->log_afam);
         e->log_best = nullptr; e->log_pose = e->log_sfam = e->log_afam = nullptr;
         e->log_cap = 0;
@@ -992,6 +999,7 @@ static StepArgs make_step_args(nvb_engine *e, int fake, int log_afam)
     s.log_afam = log_afam ? e->log_afam : nullptr;
     s.pending_fail = e->d_pending;
     s.dbg = e->d_dbg;
+    s.dmin2 = e->d_dmin2;
     return s;
 }
 
@@ -1122,6 +1130,15 @@ static int phase3(nvb_engine *e, const StepArgs &s)
 {
     int xrc = p2p_exchange(e, e->d_exact);         // exact differences: MIN over ranks before the move
     if (xrc) return xrc;
+    if (e->n_path > NVB_PATH_SPLIT && !s.fake) {
+        // long training path: pose update | grid-wide distance scan | bookkeeping
+        const int chunks = (e->n_path + NVB_PATH_CHUNK - 1) / NVB_PATH_CHUNK;
+        CK(launch_seq(k3_move_pose, dim3(e->B), dim3(NVB_STEP_THREADS), 0, e->stream, s));
+        CK(launch_seq(k3_path_scan, dim3(chunks, e->B), dim3(256), 0, e->stream, s));
+        CK(launch_seq(k3_move_finish, dim3(e->B), dim3(NVB_STEP_THREADS), 0, e->stream, s));
+        e->launches += 3;
+        return NVB_OK;
+    }
     k3_move<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
     e->launches++;
     CK(cudaGetLastError());
@@ -1250,7 +1267,10 @@ static int run_steps(nvb_engine *e, int nsteps, int fake, int log_afam, bool eag
             if ((rc = launch_sampler(e, agent_sampler_args(e), e->B))) return rc;
             e->glimpses_pending = true;
         }
-        const int per_step = fused_step(e) ? (step_form() == 3 ? 4 : step_form() == 2 ? 3 : 2) : 5;   // K2, step+sample | K1, K2, decide, ties, move
+        // launches per step-batch: K2, decide, ties, move+sample | K1, K2, decide, ties, move
+        // (+2 for the long-path move, +2 for the NVLink exchanges)
+        const int per_step = fused_step(e) ? (step_form() == 3 ? 4 : step_form() == 2 ? 3 : 2)
+                                           : 5 + (e->n_path > NVB_PATH_SPLIT && !fake ? 2 : 0) + (e->p2p_on ? 2 : 0);
         for (int i = done; i < nsteps; i++) {
             CK(cudaGraphLaunch(e->graph_exec, e->stream));
             e->launches += per_step;

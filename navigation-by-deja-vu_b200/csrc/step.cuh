@@ -67,6 +67,7 @@ struct StepArgs {
     double *log_afam;            // [cap][B][A] or nullptr
     int32_t *pending_fail;       // [B] failure the sampler found for the NEXT step, or nullptr
     long long *dbg;              // tuning aid (see SamplerArgs::dbg), else nullptr
+    unsigned long long *dmin2;   // [B] squared distance to the path (FP64 bits), long-path form
 };
 
 #define NVB_STEP_THREADS 128   /* == NVB_SAMPLER_THREADS: k31_step_sample runs both bodies */
@@ -264,6 +265,11 @@ __device__ __forceinline__ void nvb_decide(const StepArgs &a, int b, unsigned lo
 // nullptr) / a.exact hold the exact differences.  Returns through *pose_out the
 // new pose and whether the agent will take another step (status still 0 and
 // budget left); every thread gets the same answer.
+// MODE 0: everything.  Long training paths (n_path > NVB_PATH_SPLIT) are scanned grid-wide
+// instead of by the agent's own CTA: MODE 1 stops after the pose update (k3_move_pose),
+// k3_path_scan reduces the squared distances into a.dmin2, MODE 2 (k3_move_finish) resumes
+// with the bookkeeping.
+template <int MODE>
 __device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigned long long *s_exact,
                                          double *pose_out)
 {
@@ -285,7 +291,10 @@ __device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigne
         budget = a.ag.budget[b];
     }
 
-    if (tid == 0) {
+    if (MODE == 2 && tid == 0) {
+        s_pose[0] = a.ag.poses[3 * b]; s_pose[1] = a.ag.poses[3 * b + 1]; s_pose[2] = a.ag.poses[3 * b + 2];
+    }
+    if (MODE != 2 && tid == 0) {
         // angle_familiarity[k] = maxfam - diff (util.pyx:73, NavBySceneFamiliarity.py:313);
         // first maximum wins (:315)
         int best = 0;
@@ -322,6 +331,10 @@ __device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigne
     __syncthreads();
     pose_out[0] = s_pose[0]; pose_out[1] = s_pose[1]; pose_out[2] = s_pose[2];
     if (a.fake) return s_more != 0;
+    if (MODE == 1) {
+        if (tid == 0) a.dmin2[b] = 0x7FF0000000000000ull;   // +inf: k3_path_scan takes the minimum
+        return false;
+    }
 
     // update_error, :252-276.  min over sqrt(d2) == sqrt(min d2) (sqrt is monotone and
     // correctly rounded), so reduce d2 and take one sqrt.  Coverage (:272-276) marks
@@ -337,21 +350,25 @@ __device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigne
     const bool one_pass = thr <= a.max_dist;
     const double2 *path = reinterpret_cast<const double2 *>(a.path);
     double m = __longlong_as_double(0x7FF0000000000000ll);
+    if (MODE == 2) {
+        m = __longlong_as_double((long long)a.dmin2[b]);
+    } else {
 #pragma unroll 4
-    for (int n = tid; n < a.n_path; n += NVB_STEP_THREADS) {
-        const double2 pt = __ldg(path + n);
-        const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
-        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-        m = fmin(m, d2);
-        if (one_pass && d2 <= thr2) a.ag.coverage[(size_t)b * a.n_path + n] = 1;
+        for (int n = tid; n < a.n_path; n += NVB_STEP_THREADS) {
+            const double2 pt = __ldg(path + n);
+            const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            m = fmin(m, d2);
+            if (one_pass && d2 <= thr2) a.ag.coverage[(size_t)b * a.n_path + n] = 1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        if ((tid & 31) == 0) s_red[tid >> 5] = m;
+        __syncthreads();
+        m = s_red[0];
+#pragma unroll
+        for (int wq = 1; wq < NVB_STEP_THREADS / 32; wq++) m = fmin(m, s_red[wq]);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-    if ((tid & 31) == 0) s_red[tid >> 5] = m;
-    __syncthreads();
-    m = s_red[0];
-#pragma unroll
-    for (int wq = 1; wq < NVB_STEP_THREADS / 32; wq++) m = fmin(m, s_red[wq]);
     const double dmin = __dsqrt_rn(m);
     if (tid == 0) {
         int go = 1, more = 0;
@@ -436,7 +453,7 @@ k3_step(StepArgs a)
     nvb_decide<true>(a, b, s_exact, s_div);
     __syncthreads();
     double pose[3];
-    nvb_move(a, b, s_exact, pose);
+    nvb_move<0>(a, b, s_exact, pose);
 }
 
 // ---- one launch: decide + ties + move of step t, then the glimpses of step t+1 ----
@@ -462,7 +479,7 @@ k31_step_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArg
     __syncthreads();
     if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 2] = clock64();
     double pose[3];
-    const bool more = nvb_move(a, b, s_exact, pose);
+    const bool more = nvb_move<0>(a, b, s_exact, pose);
     if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 3] = clock64();
     if (!more) return;
     __syncthreads();
@@ -632,7 +649,7 @@ k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs
         return;
     }
     double pose[3];
-    const bool more = nvb_move(a, b, nullptr, pose);
+    const bool more = nvb_move<0>(a, b, nullptr, pose);
     if (!more) return;
     __syncthreads();
     nvb_sample_body<NEED_HS, PH, PW>(&tmap, sa, b, pose[0], pose[1], pose[2], smem_k3ms, a.pending_fail + b);
@@ -686,9 +703,65 @@ k3_move(StepArgs a)
         return;
     }
     double pose[3];
-    nvb_move(a, b, nullptr, pose);
+    nvb_move<0>(a, b, nullptr, pose);
 }
 
+
+// ---- long training paths: the distance scan of update_error spread over the grid ----
+#define NVB_PATH_SPLIT 16384      /* paths longer than this use the three-kernel move */
+#define NVB_PATH_CHUNK 8192       /* path points per CTA of k3_path_scan */
+
+__global__ void __launch_bounds__(NVB_STEP_THREADS)
+k3_move_pose(StepArgs a)
+{
+    nvb_grid_dep_wait();
+    const int b = blockIdx.x;
+    if (!a.ag.stepped[b]) {
+        nvb_log_idle(a, b);
+        return;
+    }
+    double pose[3];
+    nvb_move<1>(a, b, nullptr, pose);
+}
+
+__global__ void __launch_bounds__(256)
+k3_path_scan(StepArgs a)
+{
+    nvb_grid_dep_wait();
+    const int b = blockIdx.y;
+    if (!a.ag.stepped[b] || a.fake) return;
+    const double x = a.ag.poses[3 * b], y = a.ag.poses[3 * b + 1];
+    const double thr = __dmul_rn(a.coverage_factor, a.step_size);
+    double thr2 = __dmul_rn(thr, thr);
+    while (__dsqrt_rn(thr2) > thr) thr2 = __longlong_as_double(__double_as_longlong(thr2) - 1);
+    while (__dsqrt_rn(__longlong_as_double(__double_as_longlong(thr2) + 1)) <= thr)
+        thr2 = __longlong_as_double(__double_as_longlong(thr2) + 1);
+    const bool one_pass = thr <= a.max_dist;
+    const double2 *path = reinterpret_cast<const double2 *>(a.path);
+    const int n0 = blockIdx.x * NVB_PATH_CHUNK, n1 = min(n0 + NVB_PATH_CHUNK, a.n_path);
+    double m = __longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll 4
+    for (int n = n0 + threadIdx.x; n < n1; n += 256) {
+        const double2 pt = __ldg(path + n);
+        const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
+        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        m = fmin(m, d2);
+        if (one_pass && d2 <= thr2) a.ag.coverage[(size_t)b * a.n_path + n] = 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(a.dmin2 + b, (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void __launch_bounds__(NVB_STEP_THREADS)
+k3_move_finish(StepArgs a)
+{
+    nvb_grid_dep_wait();
+    const int b = blockIdx.x;
+    if (!a.ag.stepped[b]) return;
+    double pose[3];
+    nvb_move<2>(a, b, nullptr, pose);
+}
 
 // ---- MIN exchange over NVLink peer memory (view-sharded library, one process per GPU) ----
 // Every rank owns an exchange area {flags[NVB_P2P_MAX_RANKS], data[2][cap]} that its peers

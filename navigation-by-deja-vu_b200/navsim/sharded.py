@@ -18,6 +18,11 @@ Keys and exact differences are non-negative when read as int64, so a plain
 MIN reduction on int64 works (torch.distributed / NCCL ncclMin); the lowest
 global view index wins ties deterministically.
 
+Two ways to run the exchange: `ShardedStepper` below (host-driven phases, a
+torch.distributed MIN all-reduce between them), or `NavEngine.p2p_attach()` after
+which `NavEngine.step()` runs the whole sharded sequence on the device with the
+exchange done by a kernel over NVLink peer memory (csrc/step.cuh, k_p2p_min).
+
 `ShardedStepper` drives any engine-like object exposing phase(k),
 keys_tensor() and exact_tensor(); NavEngine provides them on the GPU, the CPU
 tests plug in a stand-in to exercise this logic over gloo.
