@@ -1,0 +1,109 @@
+"""Turns the raw files of tools/evidence_run.sh (gpurun_out/<tag>_*) into the tracked
+summaries under profiles/:  python tools/summarize_profiles.py r01
+Needs `ncu` on PATH to read the .ncu-rep files (no GPU needed)."""
+import collections
+import csv
+import io
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+PROF = os.path.join(ROOT, "profiles")
+
+METRICS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__cycles_elapsed.max", "sm__cycles_active.avg",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+    "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio",
+    "smsp__average_warp_latency_issue_stalled_barrier.ratio",
+    "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio",
+    "smsp__average_warp_latency_issue_stalled_wait.ratio",
+    "smsp__average_warp_latency_issue_stalled_not_selected.ratio",
+]
+
+UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def launches(tag):
+    rows = [r for r in csv.reader(open(os.path.join(OUT, tag + "_launches.csv"))) if len(r) > 14 and r[0].isdigit()]
+    per = collections.OrderedDict()
+    for r in rows:
+        per.setdefault(r[4], []).append(float(r[14]) / 1e3)
+    return per
+
+
+def raw_page(rep):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    head, units = rows[0], rows[1]
+    return head, units, rows[2:]
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    per = launches(tag)
+    shutil.copy(os.path.join(OUT, tag + "_launches.csv"), os.path.join(PROF, tag + "_launches.csv"))
+    bench = json.load(open(os.path.join(OUT, tag + "_bench_n1.json")))
+    with open(os.path.join(PROF, tag + "_launch_summary.txt"), "w") as f:
+        f.write("# per-kernel device time from profiles/%s_launches.csv\n" % tag)
+        f.write("# (ncu --metrics gpu__time_duration.sum --clock-control none on `bench.py --steps 20 --warmup 3 --quick --no-cpu`;\n")
+        f.write("#  cold-cache, serialised, no programmatic-dependent-launch overlap: compare SHARES, not absolutes)\n\n")
+        step = {}
+        for k, v in per.items():
+            f.write("%-72s n=%4d mean=%8.2f us\n" % (k[:72], len(v), sum(v) / len(v)))
+            for key in ("k2_sad_v", "k3_decide", "k3_ties", "k3_move_sample"):
+                if key in k:
+                    step[key] = sum(v) / len(v)
+        tot = sum(step.values())
+        f.write("\nsteady-state step-batch = " + " + ".join(step) + " = %.1f us under ncu\n" % tot)
+        f.write("shares: " + ", ".join("%s %.1f %%" % (k, 100 * v / tot) for k, v in step.items()) + "\n")
+        r = bench["roofline"]
+        f.write("bench.py (CUDA events, same build, no profiler): K2 %.1f us of a %.1f us L2-warm / %.1f us cold-L2 step-batch = %.1f %% / %.1f %%\n"
+                % (r["launch_ms"] * 1e3, bench["ms_per_step_l2_warm"] * 1e3, bench["ms_per_step"] * 1e3,
+                   100 * r["launch_ms"] / bench["ms_per_step_l2_warm"], 100 * r["launch_ms"] / bench["ms_per_step"]))
+        f.write("(the k3 kernels gain more from a warm L2 and from overlapping their prologue with the previous\n"
+                " kernel's tail than K2 does, which is why K2's share is larger in the live run than under ncu)\n")
+    traffic = None
+    with open(os.path.join(PROF, tag + "_ncu_summary.txt"), "w") as f:
+        f.write("# ncu --set full --clock-control none --import-source on, C2 workload (bench.py --quick), one launch each\n")
+        for rep in (tag + "_k2.ncu-rep", tag + "_k3.ncu-rep"):
+            path = os.path.join(OUT, rep)
+            if not os.path.exists(path):
+                continue
+            head, units, rows = raw_page(path)
+            for row in rows:
+                f.write("\n== %s  (%s)\n" % (row[head.index("Kernel Name")], rep))
+                for m in METRICS:
+                    if m in head:
+                        i = head.index(m)
+                        f.write("  %-72s %s %s\n" % (m, row[i], units[i]))
+                if "k2_sad_v" in row[head.index("Kernel Name")] and traffic is None:
+                    rd, wr = head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum")
+                    traffic = float(row[rd]) * UNIT_SCALE[units[rd]] + float(row[wr]) * UNIT_SCALE[units[wr]]
+    if traffic is not None:
+        json.dump({"dram_bytes_per_launch": traffic,
+                   "source": "profiles/%s_ncu_summary.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
+                             "one launch of k2_sad_v on C2)" % tag},
+                  open(os.path.join(PROF, "k2_traffic.json"), "w"))
+    for name in ("_bench_n1.json", "_bench_reference_arm.json"):
+        shutil.copy(os.path.join(OUT, tag + name), os.path.join(PROF, tag + name))
+    tail = open(os.path.join(OUT, tag + "_pytest_gpu.log")).read().strip().splitlines()[-1]
+    open(os.path.join(PROF, tag + "_pytest_gpu.txt"), "w").write("python -m pytest tests -m gpu -x -q  (B200, this build)\n" + tail + "\n")
+    print("traffic", traffic)
+
+
+if __name__ == "__main__":
+    main()
