@@ -64,6 +64,14 @@ __device__ __forceinline__ void nvb_grid_dep_wait()
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// Lets the NEXT kernel of the stream become resident as soon as every CTA of this one has
+// got here (instead of when this grid has drained): its CTAs fill the SMs this grid leaves
+// free, run their prologue -- which may only READ data no kernel of the step sequence
+// writes (library, path, tables) -- and then block in nvb_grid_dep_wait().
+__device__ __forceinline__ void nvb_grid_dep_launch()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 // ---- mbarrier / TMA helpers (inline PTX; sm_100a) -------------------------
 __device__ __forceinline__ uint32_t nvb_smem_u32(const void *p)

@@ -36,6 +36,7 @@ struct DistArgs {
     unsigned long long *keys;     // [G], pre-set to ~0
     double cw;
     int idx_bits;
+    int pdl_early;                // trigger the dependent launch at the top of the kernel
 };
 
 #define NVB_DIST_THREADS 256
@@ -112,6 +113,34 @@ k2_sad_v(DistArgs a)
         }
         __syncthreads();
     }
+    if (a.pdl_early) nvb_grid_dep_launch();
+    // spans, the library and the tile geometry are not written by any kernel of the step
+    // sequence: a CTA that became resident early starts fetching its first view tiles here
+    const int u0 = a.spans[blockIdx.x], u1 = a.spans[blockIdx.x + 1];
+    const int nk = BULK ? 1 : a.nk;
+    const int total = (u1 - u0) * nk;
+
+    // (gt, vt, kc) of the next job to LOAD, advanced incrementally (no divisions in the loop)
+    int l_gt = u0 / a.n_vt, l_vt = u0 - l_gt * a.n_vt, l_kc = 0, l_it = 0;
+    // BULK, thread 0: the two bulk copies of job (g_t, v_t) into `slot`.  The view part arms
+    // the stage's barrier for both parts, so it is always issued first.
+    auto issue_bulk = [&](int g_t, int v_t, int slot, bool part_v, bool part_g) {
+        uint8_t *st = smem + slot * C::STAGE_BYTES;
+        const int rows_g = min(TG, a.G - g_t * TG), rows_v = min(TN, a.N - v_t * TN);
+        if (part_v) {
+            nvb_mbar_expect_tx(full + slot, (uint32_t)((rows_g + rows_v) * KC));
+            nvb_bulk_load_1d(st + TG * KC, a.lv + (size_t)v_t * TN * KC, (uint32_t)(rows_v * KC), full + slot);
+        }
+        if (part_g)
+            nvb_bulk_load_1d(st, a.gv + (size_t)g_t * TG * KC, (uint32_t)(rows_g * KC), full + slot);
+    };
+    if (BULK && tid == 0) {
+        int g_t = l_gt, v_t = l_vt;
+        for (int s = 0; s < STAGES - 1 && s < total; s++) {
+            issue_bulk(g_t, v_t, s, true, false);
+            if (++v_t == a.n_vt) { v_t = 0; g_t++; }
+        }
+    }
     nvb_grid_dep_wait();   // everything above overlaps the previous kernel's tail
     if (a.step_counter != nullptr && blockIdx.x == 0 && tid == 0) {
         // one step-batch = one launch of this kernel: next log slot, empty tie list
@@ -119,24 +148,12 @@ k2_sad_v(DistArgs a)
         *a.step_counter += 1;
         *a.tie_count = 0;
     }
-    const int u0 = a.spans[blockIdx.x], u1 = a.spans[blockIdx.x + 1];
-    const int nk = BULK ? 1 : a.nk;
-    const int total = (u1 - u0) * nk;
     if (total <= 0) return;
 
-    // (gt, vt, kc) of the next job to LOAD, advanced incrementally (no divisions in the loop)
-    int l_gt = u0 / a.n_vt, l_vt = u0 - l_gt * a.n_vt, l_kc = 0, l_it = 0;
     auto load_next = [&]() {
         uint8_t *st = smem + (l_it % STAGES) * C::STAGE_BYTES;
         if (BULK) {
-            if (tid == 0) {
-                const int rows_g = min(TG, a.G - l_gt * TG), rows_v = min(TN, a.N - l_vt * TN);
-                nvb_mbar_expect_tx(full + (l_it % STAGES), (uint32_t)((rows_g + rows_v) * KC));
-                nvb_bulk_load_1d(st, a.gv + (size_t)l_gt * TG * KC, (uint32_t)(rows_g * KC),
-                                 full + (l_it % STAGES));
-                nvb_bulk_load_1d(st + TG * KC, a.lv + (size_t)l_vt * TN * KC, (uint32_t)(rows_v * KC),
-                                 full + (l_it % STAGES));
-            }
+            if (tid == 0) issue_bulk(l_gt, l_vt, l_it % STAGES, true, true);
         } else {
             const int kbyte = l_kc * KC;
             for (int q = tid; q < (TG + TN) * CPR; q += NVB_DIST_THREADS) {
@@ -181,10 +198,19 @@ k2_sad_v(DistArgs a)
 #pragma unroll
     for (int j = 0; j < MV; j++) { int r = tx + TX * j; voff[j] = TG * KC + r * KC; vsw[j] = nvb_swz<CPR>(r) << 4; }
 
+    if (BULK) {
+        // the view tiles of these jobs are already in flight: add the glimpse tiles
+        for (int s = 0; s < STAGES - 1 && s < total; s++) {
+            if (tid == 0) issue_bulk(l_gt, l_vt, s, false, true);
+            l_it++;
+            if (++l_vt == a.n_vt) { l_vt = 0; l_gt++; }
+        }
+    } else {
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < total) load_next();
-        if (!BULK) nvb_cp_async_commit();
+        for (int s = 0; s < STAGES - 1; s++) {
+            if (s < total) load_next();
+            nvb_cp_async_commit();
+        }
     }
 
     constexpr int RW = (TX < 32) ? TX : 32;

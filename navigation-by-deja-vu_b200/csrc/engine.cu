@@ -6,6 +6,7 @@
 // mode, read the two reduction buffers through nvb_device_ptr().
 // There is no CPU fallback: without an sm_100 device nvb_engine_create fails.
 #include <math.h>
+#include <cmath>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -145,6 +146,14 @@ static bool split_step() { return step_form() != 1; }
 static bool use_pdl()
 {
     static const bool v = getenv("NAVSIM_B200_NO_PDL") == nullptr;
+    return v;
+}
+
+// Every kernel of the step sequence releases its dependent at its top
+// (griddepcontrol.launch_dependents), so the next kernel's CTAs fill SMs as they free up.
+static bool early_trigger()
+{
+    static const bool v = use_pdl() && getenv("NAVSIM_B200_NO_EARLY_TRIGGER") == nullptr;
     return v;
 }
 
@@ -552,6 +561,7 @@ static int launch_distance(nvb_engine *e, int G, bool bump_step = false)
     da.keys = e->d_keys;
     da.cw = e->cw;
     da.idx_bits = (e->cw == 0.0) ? 32 : 28;
+    da.pdl_early = (bump_step && early_trigger()) ? 1 : 0;
     if (e->cw != 0.0) {
         const size_t smem = (size_t)3 * NVB_HSV_TG * e->Ppad;
         static size_t attr_set[64] = {0};
@@ -1000,6 +1010,17 @@ static StepArgs make_step_args(nvb_engine *e, int fake, int log_afam)
     s.pending_fail = e->d_pending;
     s.dbg = e->d_dbg;
     s.dmin2 = e->d_dmin2;
+    s.pdl_early = early_trigger() ? 1 : 0;
+    {   // thr2 = the largest double whose (correctly rounded) square root is <= thr, so that
+        // d2 <= thr2  <=>  sqrt(d2) <= thr  (NavBySceneFamiliarity.py:271-276)
+        const double thr = e->cvf * e->step_size;
+        double thr2 = thr * thr;
+        if (thr2 > 0.0 && std::isfinite(thr2)) {
+            while (std::sqrt(thr2) > thr) thr2 = std::nextafter(thr2, 0.0);
+            while (std::sqrt(std::nextafter(thr2, INFINITY)) <= thr) thr2 = std::nextafter(thr2, INFINITY);
+        }
+        s.cover_thr2 = thr2;
+    }
     return s;
 }
 

@@ -37,7 +37,7 @@ struct SamplerArgs {
 __host__ __device__ inline size_t nvb_sampler_smem(int BW, int BH, int nplanes, int A)
 {
     size_t win = (size_t)nvb_round_up(BW * BH, 128) * (size_t)nplanes;
-    return win + (size_t)A * 16 + 64 + 768;   // + mbarrier + quantisation tables
+    return win + (size_t)A * 24 + 64 + 768;   // + rotations (FP64 and FP32) + mbarrier + quantisation tables
 }
 
 // Sample coordinates (util.pyx:159-168).  The reference evaluates
@@ -146,7 +146,23 @@ __device__ __noinline__ int nvb_block_careful(const BlockCtx &c, float cf, float
 // NavBySceneFamiliarity.py:156-158) or -3 (IndexError, util.pyx:165-168) to
 // *fail_out and produces no (or partial) glimpses.
 // PH, PW: landscape pixels per sensor pixel known at compile time (0 = runtime).
-template <bool NEED_HS, int PH, int PW>
+// Shared-memory home of the quantisation tables [3][256] (see the layout in nvb_sample_body)
+// and their copy from global memory; a kernel that calls nvb_sample_body late may stage
+// them early (they are constant) and pass LUT_STAGED = true.
+template <bool NEED_HS>
+__device__ __forceinline__ uint8_t *nvb_sampler_lut_smem(const NvbWorld &w, int A, uint8_t *smem)
+{
+    constexpr int nplanes = NEED_HS ? 3 : 1;
+    const size_t plane_sz = (w.R > 0) ? (size_t)nvb_round_up(w.BW * w.BH, 128) : 0;
+    return smem + plane_sz * nplanes + (size_t)A * 16 + 8;
+}
+__device__ __forceinline__ void nvb_sampler_stage_lut(const NvbWorld &w, uint8_t *lut_sm)
+{
+    for (int k = threadIdx.x; k < 768 / 4; k += blockDim.x)
+        reinterpret_cast<uint32_t *>(lut_sm)[k] = __ldg(reinterpret_cast<const uint32_t *>(w.lut) + k);
+}
+
+template <bool NEED_HS, int PH, int PW, bool LUT_STAGED = false>
 __device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const SamplerArgs &a, int b,
                                                 double x, double y, double ang, uint8_t *smem,
                                                 int32_t *fail_out)
@@ -162,6 +178,7 @@ __device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const S
     double *cs_sm = (double *)(smem + plane_sz * nplanes);
     uint64_t *mbar = (uint64_t *)(cs_sm + 2 * a.A);
     uint8_t *lut_sm = (uint8_t *)(mbar + 1);     // [3][256]
+    float2 *csf_sm = (float2 *)(lut_sm + 768);   // the rotations again, rounded to FP32 for the fast path
 
     __shared__ int s_err;
 
@@ -191,8 +208,7 @@ __device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const S
     }
     // while the window is in flight: quantisation tables -> shared memory, keys reset,
     // per-heading rotation (util.pyx:143-145)
-    for (int k = tid; k < 768 / 4; k += blockDim.x)
-        reinterpret_cast<uint32_t *>(lut_sm)[k] = __ldg(reinterpret_cast<const uint32_t *>(w.lut) + k);
+    if (!LUT_STAGED) nvb_sampler_stage_lut(w, lut_sm);
     if (a.keys != nullptr)
         for (int k = tid; k < a.A; k += blockDim.x) a.keys[(size_t)b * a.A + k] = NVB_KEY_NONE;
     for (int k = tid; k < a.A; k += blockDim.x) {
@@ -208,6 +224,7 @@ __device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const S
         }
         cs_sm[2 * k] = c;
         cs_sm[2 * k + 1] = s;
+        csf_sm[k] = make_float2((float)c, (float)s);
     }
     if (a.dbg && tid == 0) a.dbg[b * 8 + 4] = clock64();
     __syncthreads();
@@ -243,18 +260,19 @@ __device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const S
         // it = k * P + bi * W + bj  (small integers: the float quotients are exact)
         const int k = (int)(((float)it + 0.5f) * inv_p), p = it - k * w.P;
         const int bi = (int)(((float)p + 0.5f) * inv_w), bj = p - bi * w.W;
-        c.q.c = cs_sm[2 * k]; c.q.s = cs_sm[2 * k + 1];
-        const float cf = (float)c.q.c, sf = (float)c.q.s;
+        const float2 csf = csf_sm[k];
+        const float cf = csf.x, sf = csf.y;
         const int row0 = bi * ph, col0 = bj * pw;
         int sum_v = 0, n = 0;
         uint8_t hh[NEED_HS ? NVB_MAX_BLOCK_PX : 1], ss[NEED_HS ? NVB_MAX_BLOCK_PX : 1];
         bool done = false;
         if (safe) {
             // lean path: no branches; the largest distance from a rounding tie seen in
-            // the block decides afterwards whether the careful path must redo it
+            // the block decides afterwards whether it must be redone
             // (sm_100 packed FP32x2: x and y coordinate advance, round and compare together)
             const float px0 = (float)col0 - half_wf, py0 = (float)row0 - half_hf;
-            float2 t_row = make_float2(fmaf(px0, cf, fmaf(-py0, sf, c.xf)), fmaf(px0, sf, fmaf(py0, cf, c.yf)));
+            const float2 t_row0 = make_float2(fmaf(px0, cf, fmaf(-py0, sf, c.xf)), fmaf(px0, sf, fmaf(py0, cf, c.yf)));
+            float2 t_row = t_row0;
             const float2 step_j = make_float2(cf, sf), step_i = make_float2(-sf, cf);
             const float2 magic = make_float2(NVB_RND_MAGIC, NVB_RND_MAGIC);
             const float2 neg_magic = make_float2(-NVB_RND_MAGIC, -NVB_RND_MAGIC), neg_one = make_float2(-1.0f, -1.0f);
@@ -272,10 +290,41 @@ __device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const S
                 }
                 t_row = __fadd2_rn(t_row, step_i);
             }
-            done = worst < c.tie;
+            if (worst >= c.tie) {
+                // rare (a few blocks in ten thousand): some sample sits within the band of a
+                // rounding tie.  Same coordinates again, one sample at a time; only the
+                // samples inside the band pay for the reference's FP64 expression.
+                if (a.dbg) atomicAdd((unsigned long long *)a.dbg + b * 8 + 7, 1ull);
+                c.q.c = cs_sm[2 * k]; c.q.s = cs_sm[2 * k + 1];
+                sum_v = 0;
+                t_row = t_row0;
+#pragma unroll 1
+                for (int i = 0; i < ph; i++) {
+                    float2 t = t_row;
+#pragma unroll 1
+                    for (int j = 0; j < pw; j++) {
+                        const float2 u = __fadd2_rn(t, magic);
+                        const float2 e = __ffma2_rn(__fadd2_rn(u, neg_magic), neg_one, t);
+                        int o = __float_as_int(u.y) * w.BW + __float_as_int(u.x) + kbase;
+                        if (!(fmaxf(fabsf(e.x), fabsf(e.y)) < c.tie)) {
+                            int ix, iy;
+                            if (nvb_sample_exact(c.q, col0 + j, row0 + i, ix, iy)) {
+                                o = (iy - oy) * w.BW + (ix - ox);
+                            } else {   // cannot happen for a `safe` agent
+                                err = 1;
+                                o = 0;
+                            }
+                        }
+                        sum_v += win_v[o];
+                        t = __fadd2_rn(t, step_j);
+                    }
+                    t_row = __fadd2_rn(t_row, step_i);
+                }
+            }
+            done = true;
         }
         if (!done) {
-            if (a.dbg) atomicAdd((unsigned long long *)a.dbg + b * 8 + 7, 1ull);
+            c.q.c = cs_sm[2 * k]; c.q.s = cs_sm[2 * k + 1];
             sum_v = nvb_block_careful<NEED_HS>(c, cf, sf, col0, row0, hh, ss, &n, &err);
         }
         // util.pyx:121-123: V = (uint8) round(sum / (fr*fc)), half away from zero.  In

@@ -68,6 +68,8 @@ struct StepArgs {
     int32_t *pending_fail;       // [B] failure the sampler found for the NEXT step, or nullptr
     long long *dbg;              // tuning aid (see SamplerArgs::dbg), else nullptr
     unsigned long long *dmin2;   // [B] squared distance to the path (FP64 bits), long-path form
+    int pdl_early;               // trigger the dependent launch at the top of every kernel
+    double cover_thr2;           // largest double whose sqrt is <= coverage_factor * step_size (host)
 };
 
 #define NVB_STEP_THREADS 128   /* == NVB_SAMPLER_THREADS: k31_step_sample runs both bodies */
@@ -343,10 +345,7 @@ __device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigne
     // the same pass, comparing d2 with thr2 = the largest double whose sqrt is <= thr.
     const double x = s_pose[0], y = s_pose[1];
     const double thr = __dmul_rn(a.coverage_factor, a.step_size);   // :271
-    double thr2 = __dmul_rn(thr, thr);
-    while (__dsqrt_rn(thr2) > thr) thr2 = __longlong_as_double(__double_as_longlong(thr2) - 1);
-    while (__dsqrt_rn(__longlong_as_double(__double_as_longlong(thr2) + 1)) <= thr)
-        thr2 = __longlong_as_double(__double_as_longlong(thr2) + 1);
+    const double thr2 = a.cover_thr2;
     const bool one_pass = thr <= a.max_dist;
     const double2 *path = reinterpret_cast<const double2 *>(a.path);
     double m = __longlong_as_double(0x7FF0000000000000ll);
@@ -439,6 +438,7 @@ __device__ __forceinline__ void nvb_commit_pending(const StepArgs &a, int b)
 __global__ void __launch_bounds__(NVB_STEP_THREADS, 8)
 k3_step(StepArgs a)
 {
+    if (a.pdl_early) nvb_grid_dep_launch();
     nvb_grid_dep_wait();
     __shared__ unsigned long long s_exact[NVB_STEP_MAX_A_SMEM];
     __shared__ double s_div[256];
@@ -462,6 +462,7 @@ template <bool NEED_HS, int PH, int PW>
 __global__ void __launch_bounds__(NVB_STEP_THREADS, 8)   // 1024 agents = 7 CTAs per SM: one wave
 k31_step_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs sa)
 {
+    if (a.pdl_early) nvb_grid_dep_launch();
     nvb_grid_dep_wait();
     extern __shared__ __align__(128) uint8_t smem_k31[];
     __shared__ unsigned long long s_exact[NVB_STEP_MAX_A_SMEM];
@@ -553,6 +554,7 @@ __device__ __forceinline__ int nvb_tie_sweep(const StepArgs &a, int slot, int n_
 __global__ void __launch_bounds__(NVB_STEP_THREADS, 8)
 k3_decide_help(StepArgs a)
 {
+    if (a.pdl_early) nvb_grid_dep_launch();
     nvb_grid_dep_wait();
     __shared__ double s_div[256];
     __shared__ int s_slot0, s_nslots, s_count, s_go;
@@ -641,8 +643,15 @@ template <bool NEED_HS, int PH, int PW>
 __global__ void __launch_bounds__(NVB_STEP_THREADS, 8)
 k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs sa)
 {
-    nvb_grid_dep_wait();
+    if (a.pdl_early) nvb_grid_dep_launch();
     extern __shared__ __align__(128) uint8_t smem_k3ms[];
+    // constant data while the tie pass drains: quantisation tables -> shared memory, and the
+    // training path (every CTA of the SM scans all of it) -> L1
+    nvb_sampler_stage_lut(sa.w, nvb_sampler_lut_smem<NEED_HS>(sa.w, sa.A, smem_k3ms));
+    if (a.n_path <= 4096)
+        for (int o = threadIdx.x * 128; o < a.n_path * 16; o += NVB_STEP_THREADS * 128)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(a.path) + o));
+    nvb_grid_dep_wait();
     const int b = blockIdx.x;
     if (!a.ag.stepped[b]) {
         nvb_log_idle(a, b);
@@ -652,20 +661,23 @@ k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs
     const bool more = nvb_move<0>(a, b, nullptr, pose);
     if (!more) return;
     __syncthreads();
-    nvb_sample_body<NEED_HS, PH, PW>(&tmap, sa, b, pose[0], pose[1], pose[2], smem_k3ms, a.pending_fail + b);
+    nvb_sample_body<NEED_HS, PH, PW, true>(&tmap, sa, b, pose[0], pose[1], pose[2], smem_k3ms, a.pending_fail + b);
 }
 
 // ---- three launches (large / view-sharded libraries) -----------------------------
-__global__ void __launch_bounds__(NVB_STEP_THREADS)
+__global__ void __launch_bounds__(NVB_STEP_THREADS, 7)   // 1024 agents = 7 CTAs per SM: one wave
 k3_decide(StepArgs a)
 {
+    if (a.pdl_early) nvb_grid_dep_launch();
+    __shared__ double s_div[256];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_div[k] = a.div255[k];   // constant table
     nvb_grid_dep_wait();
     const int b = blockIdx.x;
-    nvb_commit_pending(a, b);
+    nvb_commit_pending(a, b);   // (its barrier also publishes s_div)
     const bool active = nvb_agent_active(a.ag, b);
     if (threadIdx.x == 0) a.ag.stepped[b] = active ? 1 : 0;
     if (!active) return;
-    nvb_decide<false>(a, b, nullptr, a.div255);
+    nvb_decide<false>(a, b, nullptr, s_div);
 }
 
 // Tie pass: every (tied glimpse, local view) pair whose score is within the
@@ -674,6 +686,7 @@ k3_decide(StepArgs a)
 __global__ void __launch_bounds__(NVB_TIE_THREADS)
 k3_ties(StepArgs a)
 {
+    if (a.pdl_early) nvb_grid_dep_launch();
     nvb_grid_dep_wait();
     const int n_items = *a.tie_count;
     if (n_items == 0) return;
@@ -696,6 +709,7 @@ k3_ties(StepArgs a)
 __global__ void __launch_bounds__(NVB_STEP_THREADS)
 k3_move(StepArgs a)
 {
+    if (a.pdl_early) nvb_grid_dep_launch();
     nvb_grid_dep_wait();
     const int b = blockIdx.x;
     if (!a.ag.stepped[b]) {
@@ -714,6 +728,7 @@ k3_move(StepArgs a)
 __global__ void __launch_bounds__(NVB_STEP_THREADS)
 k3_move_pose(StepArgs a)
 {
+    if (a.pdl_early) nvb_grid_dep_launch();
     nvb_grid_dep_wait();
     const int b = blockIdx.x;
     if (!a.ag.stepped[b]) {
@@ -727,15 +742,13 @@ k3_move_pose(StepArgs a)
 __global__ void __launch_bounds__(256)
 k3_path_scan(StepArgs a)
 {
+    if (a.pdl_early) nvb_grid_dep_launch();
     nvb_grid_dep_wait();
     const int b = blockIdx.y;
     if (!a.ag.stepped[b] || a.fake) return;
     const double x = a.ag.poses[3 * b], y = a.ag.poses[3 * b + 1];
     const double thr = __dmul_rn(a.coverage_factor, a.step_size);
-    double thr2 = __dmul_rn(thr, thr);
-    while (__dsqrt_rn(thr2) > thr) thr2 = __longlong_as_double(__double_as_longlong(thr2) - 1);
-    while (__dsqrt_rn(__longlong_as_double(__double_as_longlong(thr2) + 1)) <= thr)
-        thr2 = __longlong_as_double(__double_as_longlong(thr2) + 1);
+    const double thr2 = a.cover_thr2;
     const bool one_pass = thr <= a.max_dist;
     const double2 *path = reinterpret_cast<const double2 *>(a.path);
     const int n0 = blockIdx.x * NVB_PATH_CHUNK, n1 = min(n0 + NVB_PATH_CHUNK, a.n_path);
@@ -756,6 +769,7 @@ k3_path_scan(StepArgs a)
 __global__ void __launch_bounds__(NVB_STEP_THREADS)
 k3_move_finish(StepArgs a)
 {
+    if (a.pdl_early) nvb_grid_dep_launch();
     nvb_grid_dep_wait();
     const int b = blockIdx.x;
     if (!a.ag.stepped[b]) return;
