@@ -205,8 +205,15 @@ int nvb_set_options(nvb_engine *e, int use_graph, int kernel_timing);
 double nvb_kernel_time_ms(nvb_engine *e, int64_t *count);
 
 /* Tuning aid: one step-batch with per-agent clock64 checkpoints of the fused
- * step+sample kernel; out [B][8] (SM cycles; 0 = not reached). */
+ * step+sample kernel; out [2][B][8] (SM cycles; 0 = not reached): block 0 the main
+ * checkpoints, block 1 finer ones inside the move. */
 int nvb_debug_step_clocks(nvb_engine *e, long long *out);
+
+/* Tuning aid: `nsteps` step-batches as nvb_agents_step runs them, every CTA of the four
+ * step kernels (distance, decide, ties, move+sample) stamping the global timer when it
+ * becomes resident, when its grid dependency is met and when it is done.
+ * out [4][2048][3], ns, of the last step-batch; 0 = CTA not present. */
+int nvb_debug_timeline(nvb_engine *e, int nsteps, long long *out);
 
 /* Counters for bench.py: kernels launched by this engine so far. */
 int64_t nvb_launch_count(nvb_engine *e);

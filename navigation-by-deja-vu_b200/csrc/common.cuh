@@ -73,6 +73,19 @@ __device__ __forceinline__ void nvb_grid_dep_launch()
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// Tuning aid (nvb_debug_timeline): per-CTA wall-clock stamps of the step kernels,
+// tl[kernel][min(cta, NVB_TL_CTAS - 1)][3] = {resident, dependency met, done} in ns.
+#define NVB_TL_CTAS 2048
+__device__ __forceinline__ void nvb_tl_stamp(long long *tl, int kernel, int what)
+{
+    if (tl != nullptr && threadIdx.x == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const int cta = blockIdx.x < NVB_TL_CTAS ? blockIdx.x : NVB_TL_CTAS - 1;
+        tl[((size_t)kernel * NVB_TL_CTAS + cta) * 3 + what] = t;
+    }
+}
+
 // ---- mbarrier / TMA helpers (inline PTX; sm_100a) -------------------------
 __device__ __forceinline__ uint32_t nvb_smem_u32(const void *p)
 {

@@ -37,6 +37,7 @@ struct DistArgs {
     double cw;
     int idx_bits;
     int pdl_early;                // trigger the dependent launch at the top of the kernel
+    long long *tl;                // tuning aid: timeline stamps (nvb_tl_stamp) or nullptr
 };
 
 #define NVB_DIST_THREADS 256
@@ -113,6 +114,7 @@ k2_sad_v(DistArgs a)
         }
         __syncthreads();
     }
+    nvb_tl_stamp(a.tl, 0, 0);
     if (a.pdl_early) nvb_grid_dep_launch();
     // spans, the library and the tile geometry are not written by any kernel of the step
     // sequence: a CTA that became resident early starts fetching its first view tiles here
@@ -142,6 +144,7 @@ k2_sad_v(DistArgs a)
         }
     }
     nvb_grid_dep_wait();   // everything above overlaps the previous kernel's tail
+    nvb_tl_stamp(a.tl, 0, 1);
     if (a.step_counter != nullptr && blockIdx.x == 0 && tid == 0) {
         // one step-batch = one launch of this kernel: next log slot, empty tie list
         // (the kernels that read them run after this one)
@@ -315,6 +318,7 @@ k2_sad_v(DistArgs a)
             if (++vt == a.n_vt) { vt = 0; gt++; }
         }
     }
+    nvb_tl_stamp(a.tl, 0, 2);
 }
 
 // ---- chem_weight > 0: hue/saturation branch + V, three planes ----------------

@@ -101,6 +101,7 @@ struct nvb_engine {
     void *p2p_opened[NVB_P2P_MAX_RANKS] = {nullptr};
     unsigned long long *d_dmin2 = nullptr;   // [B] long-path form of update_error
     long long *d_dbg = nullptr;     // tuning aid: per-agent clock64 checkpoints of one step
+    long long *d_tl = nullptr;      // tuning aid: per-CTA wall-clock stamps of the step kernels
     int32_t *d_pending = nullptr;   // [B] sampler failure parked for the next step (fused loop)
     bool glimpses_pending = false;  // the glimpses of the next step are already sampled
     double *d_poses0 = nullptr;     // start poses / budgets kept for nvb_agents_rewind
@@ -427,10 +428,15 @@ extern "C" int nvb_set_nav_params(nvb_engine *e, double step_size, double max_di
 // FP32 error of px*c - py*s + frac(x) for |px|, |py| <= half the sensor footprint.
 static float sampler_band(const nvb_engine *e)
 {
-    // FP32 error: operand rounding ~6e-8 * footprint, two FMAs and (pw + ph) running adds
-    // of at most half an ulp of the window radius each; the band is > 3x that bound
-    const float foot = (float)(e->W * e->pw + e->H * e->ph);
-    return 4e-7f * foot + 1e-5f + 2e-8f * foot * (float)(e->pw + e->ph);
+    // Worst FP32 error of a sample coordinate t = px*c - py*s + frac(x) as sampler.cuh
+    // computes it, |t| < M:  c and s rounded to FP32 (2^-25 each, times |px| + |py|), frac(x)
+    // rounded (2^-25), two FMAs and at most (ph - 1) + (pw - 1) running adds of half an ulp
+    // of M each.  The band is 1.5 x that bound.
+    const double hx = 0.5 * e->W * e->pw, hy = 0.5 * e->H * e->ph;
+    const double M = hx + hy + 2.0;
+    const double half_ulp = ldexp(1.0, (int)floor(log2(M)) - 24);
+    const double err = (hx + hy + 1.0) * ldexp(1.0, -25) + (double)(e->ph + e->pw) * half_ulp;
+    return (float)(1.5 * err + 1e-6);
 }
 
 template <bool HS, int PH, int PW>
@@ -562,6 +568,7 @@ static int launch_distance(nvb_engine *e, int G, bool bump_step = false)
     da.cw = e->cw;
     da.idx_bits = (e->cw == 0.0) ? 32 : 28;
     da.pdl_early = (bump_step && early_trigger()) ? 1 : 0;
+    da.tl = bump_step ? e->d_tl : nullptr;
     if (e->cw != 0.0) {
         const size_t smem = (size_t)3 * NVB_HSV_TG * e->Ppad;
         static size_t attr_set[64] = {0};
@@ -1011,6 +1018,7 @@ static StepArgs make_step_args(nvb_engine *e, int fake, int log_afam)
     s.dbg = e->d_dbg;
     s.dmin2 = e->d_dmin2;
     s.pdl_early = early_trigger() ? 1 : 0;
+    s.tl = e->d_tl;
     {   // thr2 = the largest double whose (correctly rounded) square root is <= thr, so that
         // d2 <= thr2  <=>  sqrt(d2) <= thr  (NavBySceneFamiliarity.py:271-276)
         const double thr = e->cvf * e->step_size;
@@ -1094,7 +1102,13 @@ static int launch_k3ms_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa
     } else {
         k3_decide_help<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
     }
-    CK(launch_seq(k3_move_sample<HS, PH, PW>, dim3(e->B), dim3(NVB_STEP_THREADS), smem, e->stream, e->tmap, s, sa));
+    // 128 or 160 threads, whichever leaves fewer idle lanes in the gather loop over the
+    // A * P sensor pixels (the default 10 x 80 = 800 is exactly five passes of 160)
+    const long long items = (long long)e->A * e->P;
+    const long long w128 = ((items + 127) / 128) * 128, w160 = ((items + 159) / 160) * 160;
+    static const int forced = getenv("NAVSIM_B200_MS_THREADS") ? atoi(getenv("NAVSIM_B200_MS_THREADS")) : 0;
+    const int threads = forced ? forced : (w160 < w128 ? NVB_MS_MAX_THREADS : NVB_STEP_THREADS);
+    CK(launch_seq(k3_move_sample<HS, PH, PW>, dim3(e->B), dim3(threads), smem, e->stream, e->tmap, s, sa));
     if (tev) cudaEventRecord(tev[3], e->stream);
     e->launches += 2;
     CK(cudaGetLastError());
@@ -1514,8 +1528,8 @@ extern "C" int nvb_debug_step_clocks(nvb_engine *e, long long *out)
     int rc = check_step_ready(e, 0);
     if (rc) return rc;
     CK(cudaSetDevice(e->device));
-    CK(cudaMalloc(&e->d_dbg, sizeof(long long) * 8 * e->B));
-    CK(cudaMemsetAsync(e->d_dbg, 0, sizeof(long long) * 8 * e->B, e->stream));
+    CK(cudaMalloc(&e->d_dbg, sizeof(long long) * 16 * e->B));
+    CK(cudaMemsetAsync(e->d_dbg, 0, sizeof(long long) * 16 * e->B, e->stream));
     rc = run_steps(e, 1, 0, 0, false);
     if (!rc) {
         const bool g = e->use_graph;
@@ -1523,10 +1537,32 @@ extern "C" int nvb_debug_step_clocks(nvb_engine *e, long long *out)
         rc = run_steps(e, 1, 0, 0, false);
         e->use_graph = g;
     }
-    if (!rc) CK(cudaMemcpyAsync(out, e->d_dbg, sizeof(long long) * 8 * e->B, cudaMemcpyDeviceToHost, e->stream));
+    if (!rc) CK(cudaMemcpyAsync(out, e->d_dbg, sizeof(long long) * 16 * e->B, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     cudaFree(e->d_dbg);
     e->d_dbg = nullptr;
+    e->graph_dirty = true;
+    return rc;
+}
+
+// Tuning aid: `nsteps` step-batches the way nvb_agents_step runs them (graph replay), with
+// every CTA of the four step kernels stamping %globaltimer when it becomes resident, when
+// its grid dependency is met and when it is done; out [4][NVB_TL_CTAS][3] holds the stamps
+// of the LAST step-batch (ns; 0 = CTA not present).
+extern "C" int nvb_debug_timeline(nvb_engine *e, int nsteps, long long *out)
+{
+    int rc = check_step_ready(e, 0);
+    if (rc) return rc;
+    CK(cudaSetDevice(e->device));
+    const size_t n = (size_t)4 * NVB_TL_CTAS * 3;
+    CK(cudaMalloc(&e->d_tl, sizeof(long long) * n));
+    CK(cudaMemsetAsync(e->d_tl, 0, sizeof(long long) * n, e->stream));
+    e->graph_dirty = true;
+    rc = run_steps(e, nsteps, 0, 0, false);
+    if (!rc) CK(cudaMemcpyAsync(out, e->d_tl, sizeof(long long) * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_tl);
+    e->d_tl = nullptr;
     e->graph_dirty = true;
     return rc;
 }

@@ -37,7 +37,7 @@ struct SamplerArgs {
 __host__ __device__ inline size_t nvb_sampler_smem(int BW, int BH, int nplanes, int A)
 {
     size_t win = (size_t)nvb_round_up(BW * BH, 128) * (size_t)nplanes;
-    return win + (size_t)A * 24 + 64 + 768;   // + rotations (FP64 and FP32) + mbarrier + quantisation tables
+    return win + (size_t)A * 32 + 64 + 768;   // + rotations (FP64 and FP32), heading offsets, mbarrier, tables
 }
 
 // Sample coordinates (util.pyx:159-168).  The reference evaluates
@@ -146,89 +146,141 @@ __device__ __noinline__ int nvb_block_careful(const BlockCtx &c, float cf, float
 // NavBySceneFamiliarity.py:156-158) or -3 (IndexError, util.pyx:165-168) to
 // *fail_out and produces no (or partial) glimpses.
 // PH, PW: landscape pixels per sensor pixel known at compile time (0 = runtime).
-// Shared-memory home of the quantisation tables [3][256] (see the layout in nvb_sample_body)
-// and their copy from global memory; a kernel that calls nvb_sample_body late may stage
-// them early (they are constant) and pass LUT_STAGED = true.
-template <bool NEED_HS>
-__device__ __forceinline__ uint8_t *nvb_sampler_lut_smem(const NvbWorld &w, int A, uint8_t *smem)
-{
-    constexpr int nplanes = NEED_HS ? 3 : 1;
-    const size_t plane_sz = (w.R > 0) ? (size_t)nvb_round_up(w.BW * w.BH, 128) : 0;
-    return smem + plane_sz * nplanes + (size_t)A * 16 + 8;
-}
+// Copy of the quantisation tables [3][256] from global memory to their shared-memory home.
 __device__ __forceinline__ void nvb_sampler_stage_lut(const NvbWorld &w, uint8_t *lut_sm)
 {
     for (int k = threadIdx.x; k < 768 / 4; k += blockDim.x)
         reinterpret_cast<uint32_t *>(lut_sm)[k] = __ldg(reinterpret_cast<const uint32_t *>(w.lut) + k);
 }
 
-template <bool NEED_HS, int PH, int PW, bool LUT_STAGED = false>
-__device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const SamplerArgs &a, int b,
-                                                double x, double y, double ang, uint8_t *smem,
-                                                int32_t *fail_out)
+// Shared-memory layout of one sampling CTA (dynamic shared memory, nvb_sampler_smem bytes).
+struct SamplerSmem {
+    uint8_t *win_v, *win_h, *win_s;   // staged window planes
+    double *cs;                       // [A][2] cos, sin of every heading's rotation (FP64)
+    uint64_t *mbar;                   // completion barrier of the window's TMA loads
+    uint8_t *lut;                     // [3][256] quantisation tables
+    float2 *csf;                      // [A] the rotations rounded to FP32 (fast path)
+    double *offs;                     // [A] heading offsets (staged by kernels that want them close)
+    int *err;                         // IndexError flag of this CTA
+};
+
+template <bool NEED_HS>
+__device__ __forceinline__ SamplerSmem nvb_sampler_layout(const NvbWorld &w, int A, uint8_t *smem)
+{
+    constexpr int nplanes = NEED_HS ? 3 : 1;
+    const size_t plane_sz = (w.R > 0) ? (size_t)nvb_round_up(w.BW * w.BH, 128) : 0;
+    SamplerSmem L;
+    L.win_v = smem;                   // plane order in smem: V, H, S
+    L.win_h = smem + plane_sz;
+    L.win_s = smem + 2 * plane_sz;
+    L.cs = (double *)(smem + plane_sz * nplanes);
+    L.mbar = (uint64_t *)(L.cs + 2 * A);
+    L.lut = (uint8_t *)(L.mbar + 1);
+    L.csf = (float2 *)(L.lut + 768);
+    L.offs = (double *)(L.csf + A);
+    L.err = (int *)(L.offs + A);
+    return L;
+}
+
+// Step 1 (every thread): bounds test of the pose (NavBySceneFamiliarity.py:156-158; true =
+// out of bounds, nothing touched), then thread 0 starts the TMA loads of the window the
+// rotated sensor can reach; the keys of this agent's headings are reset for the next K2.
+template <bool NEED_HS>
+__device__ __forceinline__ bool nvb_sample_window(const CUtensorMap *tmap, const SamplerArgs &a, int b,
+                                                  double x, double y, const SamplerSmem &L)
 {
     const NvbWorld &w = a.w;
     const int tid = threadIdx.x;
     constexpr int nplanes = NEED_HS ? 3 : 1;
-    const int use_win = (w.R > 0);
-    const size_t plane_sz = use_win ? (size_t)nvb_round_up(w.BW * w.BH, 128) : 0;
-    uint8_t *win_v = smem;                       // plane order in smem: V, H, S
-    uint8_t *win_h = smem + plane_sz;
-    uint8_t *win_s = smem + 2 * plane_sz;
-    double *cs_sm = (double *)(smem + plane_sz * nplanes);
-    uint64_t *mbar = (uint64_t *)(cs_sm + 2 * a.A);
-    uint8_t *lut_sm = (uint8_t *)(mbar + 1);     // [3][256]
-    float2 *csf_sm = (float2 *)(lut_sm + 768);   // the rotations again, rounded to FP32 for the fast path
-
-    __shared__ int s_err;
-
-    // NavBySceneFamiliarity.py:156-158 (every thread evaluates the same test)
-    if (x <= w.r || y <= w.r || x >= (double)w.cols - w.r || y >= (double)w.rows - w.r) {
-        if (tid == 0) *fail_out = -2;
-        return;
-    }
+    if (x <= w.r || y <= w.r || x >= (double)w.cols - w.r || y >= (double)w.rows - w.r) return true;
     // TMA needs the box's innermost start coordinate on a 16-byte boundary (an
     // unaligned start traps with an illegal-instruction error on sm_100); BW has
     // 15 spare columns for that.
-    const double fx = floor(x), fy = floor(y);
-    const int xi = (int)fx, yi = (int)fy;
+    const int xi = (int)floor(x), yi = (int)floor(y);
     const int ox = (xi - w.R) & ~15, oy = yi - w.R;
     if (tid == 0) {
-        s_err = 0;
-        if (use_win) {
-            nvb_mbar_init(mbar, 1);
+        *L.err = 0;
+        if (w.R > 0) {
+            nvb_mbar_init(L.mbar, 1);
             nvb_fence_barrier_init();
-            nvb_mbar_expect_tx(mbar, (uint32_t)(w.BW * w.BH * nplanes));
-            nvb_tma_load_3d(win_v, tmap, ox, oy, 2, mbar);
+            nvb_mbar_expect_tx(L.mbar, (uint32_t)(w.BW * w.BH * nplanes));
+            nvb_tma_load_3d(L.win_v, tmap, ox, oy, 2, L.mbar);
             if (NEED_HS) {
-                nvb_tma_load_3d(win_h, tmap, ox, oy, 0, mbar);
-                nvb_tma_load_3d(win_s, tmap, ox, oy, 1, mbar);
+                nvb_tma_load_3d(L.win_h, tmap, ox, oy, 0, L.mbar);
+                nvb_tma_load_3d(L.win_s, tmap, ox, oy, 1, L.mbar);
             }
         }
     }
-    // while the window is in flight: quantisation tables -> shared memory, keys reset,
-    // per-heading rotation (util.pyx:143-145)
-    if (!LUT_STAGED) nvb_sampler_stage_lut(w, lut_sm);
     if (a.keys != nullptr)
         for (int k = tid; k < a.A; k += blockDim.x) a.keys[(size_t)b * a.A + k] = NVB_KEY_NONE;
-    for (int k = tid; k < a.A; k += blockDim.x) {
+    return false;
+}
+
+// Step 2 (threads first_thread .. first_thread + n_threads - 1): per-heading rotation
+// (util.pyx:143-145).  offsets: a.offsets or a copy of them in shared memory.
+__device__ __forceinline__ void nvb_sample_rotations(const SamplerArgs &a, int b, double ang,
+                                                     const SamplerSmem &L, const double *offsets,
+                                                     int first_thread, int n_threads)
+{
+    const int j = (int)threadIdx.x - first_thread;
+    if (j < 0 || j >= n_threads) return;
+    for (int k = j; k < a.A; k += n_threads) {
         double c, s;
         if (a.cs != nullptr) {
             c = a.cs[2 * b];
             s = a.cs[2 * b + 1];
         } else {
             double angle = ang;
-            if (a.agent_mode) angle = nvb_pymod_pos(__dadd_rn(ang, a.offsets[k]), NVB_TWO_PI);
+            if (a.agent_mode) angle = nvb_pymod_pos(__dadd_rn(ang, offsets[k]), NVB_TWO_PI);
             double rot = -__dsub_rn(0.5 * NVB_PI, angle);
             sincos(rot, &s, &c);
         }
-        cs_sm[2 * k] = c;
-        cs_sm[2 * k + 1] = s;
-        csf_sm[k] = make_float2((float)c, (float)s);
+        L.cs[2 * k] = c;
+        L.cs[2 * k + 1] = s;
+        L.csf[k] = make_float2((float)c, (float)s);
     }
+}
+
+template <bool NEED_HS, int PH, int PW>
+__device__ __forceinline__ void nvb_sample_gather(const SamplerArgs &a, int b, double x, double y,
+                                                  const SamplerSmem &L, int32_t *fail_out);
+
+// The three steps in one go.  LUT_STAGED: the caller has already copied the quantisation
+// tables to L.lut (they are constant; nvb_sampler_stage_lut).
+template <bool NEED_HS, int PH, int PW, bool LUT_STAGED = false>
+__device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const SamplerArgs &a, int b,
+                                                double x, double y, double ang, uint8_t *smem,
+                                                int32_t *fail_out)
+{
+    const SamplerSmem L = nvb_sampler_layout<NEED_HS>(a.w, a.A, smem);
+    if (nvb_sample_window<NEED_HS>(tmap, a, b, x, y, L)) {
+        if (threadIdx.x == 0) *fail_out = -2;
+        return;
+    }
+    // while the window is in flight: quantisation tables -> shared memory, rotations
+    if (!LUT_STAGED) nvb_sampler_stage_lut(a.w, L.lut);
+    nvb_sample_rotations(a, b, ang, L, a.offsets, 0, (int)blockDim.x);
+    nvb_sample_gather<NEED_HS, PH, PW>(a, b, x, y, L, fail_out);
+}
+
+// Step 3 (every thread): wait for the window, gather, block mean, quantise, mask.
+template <bool NEED_HS, int PH, int PW>
+__device__ __forceinline__ void nvb_sample_gather(const SamplerArgs &a, int b, double x, double y,
+                                                  const SamplerSmem &L, int32_t *fail_out)
+{
+    const NvbWorld &w = a.w;
+    const int tid = threadIdx.x;
+    const int use_win = (w.R > 0);
+    const uint8_t *win_v = L.win_v, *win_h = L.win_h, *win_s = L.win_s;
+    const double *cs_sm = L.cs;
+    const uint8_t *lut_sm = L.lut;
+    const float2 *csf_sm = L.csf;
+    const double fx = floor(x), fy = floor(y);
+    const int xi = (int)fx, yi = (int)fy;
+    const int ox = (xi - w.R) & ~15, oy = yi - w.R;
     if (a.dbg && tid == 0) a.dbg[b * 8 + 4] = clock64();
-    __syncthreads();
-    if (use_win) nvb_mbar_wait(mbar, 0);
+    __syncthreads();   // rotations, tables, barrier initialisation
+    if (use_win) nvb_mbar_wait(L.mbar, 0);
     if (a.dbg && tid == 0) a.dbg[b * 8 + 5] = clock64();
 
     const int ph = PH ? PH : w.ph, pw = PW ? PW : w.pw;
@@ -291,31 +343,27 @@ __device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const S
                 t_row = __fadd2_rn(t_row, step_i);
             }
             if (worst >= c.tie) {
-                // rare (a few blocks in ten thousand): some sample sits within the band of a
-                // rounding tie.  Same coordinates again, one sample at a time; only the
-                // samples inside the band pay for the reference's FP64 expression.
+                // rare (about one block in a thousand): some sample sits within the band of a
+                // rounding tie.  Same coordinates again; the samples inside the band are
+                // re-addressed with the reference's FP64 expression and the sum corrected.
                 if (a.dbg) atomicAdd((unsigned long long *)a.dbg + b * 8 + 7, 1ull);
                 c.q.c = cs_sm[2 * k]; c.q.s = cs_sm[2 * k + 1];
-                sum_v = 0;
                 t_row = t_row0;
-#pragma unroll 1
+#pragma unroll
                 for (int i = 0; i < ph; i++) {
                     float2 t = t_row;
-#pragma unroll 1
+#pragma unroll
                     for (int j = 0; j < pw; j++) {
                         const float2 u = __fadd2_rn(t, magic);
                         const float2 e = __ffma2_rn(__fadd2_rn(u, neg_magic), neg_one, t);
-                        int o = __float_as_int(u.y) * w.BW + __float_as_int(u.x) + kbase;
                         if (!(fmaxf(fabsf(e.x), fabsf(e.y)) < c.tie)) {
                             int ix, iy;
-                            if (nvb_sample_exact(c.q, col0 + j, row0 + i, ix, iy)) {
-                                o = (iy - oy) * w.BW + (ix - ox);
-                            } else {   // cannot happen for a `safe` agent
-                                err = 1;
-                                o = 0;
-                            }
+                            if (nvb_sample_exact(c.q, col0 + j, row0 + i, ix, iy))
+                                sum_v += (int)win_v[(iy - oy) * w.BW + (ix - ox)] -
+                                         (int)win_v[__float_as_int(u.y) * w.BW + __float_as_int(u.x) + kbase];
+                            else
+                                err = 1;   // cannot happen for a `safe` agent
                         }
-                        sum_v += win_v[o];
                         t = __fadd2_rn(t, step_j);
                     }
                     t_row = __fadd2_rn(t_row, step_i);
@@ -355,9 +403,9 @@ __device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const S
             a.gs[o] = masked ? 0 : lut_sm[256 + sat];
         }
     }
-    if (err) s_err = 1;
+    if (err) *L.err = 1;
     __syncthreads();
-    if (tid == 0 && s_err) *fail_out = -3;   // IndexError, util.pyx:165-168
+    if (tid == 0 && *L.err) *fail_out = -3;   // IndexError, util.pyx:165-168
     if (a.dbg && tid == 0) a.dbg[b * 8 + 6] = clock64();
 }
 

@@ -69,6 +69,7 @@ struct StepArgs {
     long long *dbg;              // tuning aid (see SamplerArgs::dbg), else nullptr
     unsigned long long *dmin2;   // [B] squared distance to the path (FP64 bits), long-path form
     int pdl_early;               // trigger the dependent launch at the top of every kernel
+    long long *tl;               // tuning aid: timeline stamps (nvb_tl_stamp) or nullptr
     double cover_thr2;           // largest double whose sqrt is <= coverage_factor * step_size (host)
 };
 
@@ -271,67 +272,122 @@ __device__ __forceinline__ void nvb_decide(const StepArgs &a, int b, unsigned lo
 // instead of by the agent's own CTA: MODE 1 stops after the pose update (k3_move_pose),
 // k3_path_scan reduces the squared distances into a.dmin2, MODE 2 (k3_move_finish) resumes
 // with the bookkeeping.
-template <int MODE>
+struct NvbNoHook {
+    __device__ __forceinline__ void operator()(const double *) const {}
+};
+
+// This agent's inputs, fetched in ONE round trip to L2 (nvb_move_preload) before anything
+// branches on them: thread 0 holds the counters and the pose, lane k of warp 0 the exact
+// difference of heading k (sweeps of up to 32 headings).
+struct MovePre {
+    int nav_frames, err_n, completed, budget, t;
+    double err_sum, px, py, ang0;
+    unsigned long long eb;
+};
+
+__device__ __forceinline__ MovePre nvb_move_preload(const StepArgs &a, int b, const unsigned long long *s_exact)
+{
+    MovePre p;
+    const int tid = threadIdx.x;
+    p.t = *a.step_counter;
+    p.nav_frames = p.err_n = p.completed = p.budget = 0;
+    p.err_sum = p.px = p.py = p.ang0 = 0.0;
+    p.eb = NVB_EXACT_NONE;
+    if (tid == 0) {
+        p.nav_frames = a.ag.nav_frames[b];
+        p.err_n = a.ag.err_n[b];
+        p.err_sum = a.ag.err_sum[b];
+        p.completed = a.ag.completed[b];
+        p.budget = a.ag.budget[b];
+        p.px = a.ag.poses[3 * b]; p.py = a.ag.poses[3 * b + 1]; p.ang0 = a.ag.poses[3 * b + 2];
+    }
+    if (a.A <= 32 && tid < a.A) p.eb = (s_exact != nullptr) ? s_exact[tid] : a.exact[(size_t)b * a.A + tid];
+    return p;
+}
+
+// AfterPose(pose): called by every thread once the new pose is published (shared memory).
+// BesideScan(pose): called by warp 1 instead of its share of the path scan when W1_HOOK
+// (the other warps scan the whole path meanwhile).
+// offsets: the heading offsets (a.offsets, or a copy of them in shared memory).
+template <int MODE, bool W1_HOOK = false, typename AfterPose = NvbNoHook, typename BesideScan = NvbNoHook>
 __device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigned long long *s_exact,
-                                         double *pose_out)
+                                         const MovePre &pre, const double *offsets, double *pose_out,
+                                         AfterPose after_pose = AfterPose(), BesideScan beside_scan = BesideScan())
 {
     const int tid = threadIdx.x;
-    const int t = *a.step_counter;
+    const int t = pre.t;
     const bool logging = (t >= 0 && t < a.log_cap);
     __shared__ int s_go, s_more;
     __shared__ double s_pose[3];
-    __shared__ double s_red[NVB_STEP_THREADS / 32];
-
-    // counters the bookkeeping at the end needs: loaded early, used late
-    int nav_frames = 0, err_n = 0, completed = 0, budget = 0;
-    double err_sum = 0.0;
-    if (tid == 0) {
-        nav_frames = a.ag.nav_frames[b];
-        err_n = a.ag.err_n[b];
-        err_sum = a.ag.err_sum[b];
-        completed = a.ag.completed[b];
-        budget = a.ag.budget[b];
-    }
+    __shared__ double s_red[8];
+    const int completed = pre.completed, budget = pre.budget;
 
     if (MODE == 2 && tid == 0) {
-        s_pose[0] = a.ag.poses[3 * b]; s_pose[1] = a.ag.poses[3 * b + 1]; s_pose[2] = a.ag.poses[3 * b + 2];
+        s_pose[0] = pre.px; s_pose[1] = pre.py; s_pose[2] = pre.ang0;
     }
-    if (MODE != 2 && tid == 0) {
+    if (MODE != 2 && tid < 32) {
         // angle_familiarity[k] = maxfam - diff (util.pyx:73, NavBySceneFamiliarity.py:313);
         // first maximum wins (:315)
-        int best = 0;
-        double best_fam = 0.0;
-        for (int k = 0; k < a.A; k++) {
-            const unsigned long long eb =
-                (s_exact != nullptr && k < NVB_STEP_MAX_A_SMEM) ? s_exact[k] : a.exact[(size_t)b * a.A + k];
-            const double fam = __dsub_rn(a.maxfam, __longlong_as_double((long long)eb));
-            if (logging && a.log_afam) a.log_afam[((size_t)t * a.B + b) * a.A + k] = fam;
-            if (k == 0 || fam > best_fam) { best = k; best_fam = fam; }
+        int best = 0x7FFFFFFF;
+        double best_fam = __longlong_as_double(0xFFF0000000000000ll);   // -inf
+        if (a.A <= 32) {
+            // a short sweep: lane k holds heading k; every lane runs the same short compare chain
+            const double fam = __dsub_rn(a.maxfam, __longlong_as_double((long long)pre.eb));
+            if (logging && a.log_afam && tid < a.A) a.log_afam[((size_t)t * a.B + b) * a.A + tid] = fam;
+            for (int k = 0; k < a.A; k++) {
+                const double fk = __shfl_sync(0xFFFFFFFFu, fam, k);
+                if (k == 0 || fk > best_fam) { best = k; best_fam = fk; }
+            }
+        } else {
+            // warp 0: lane l looks at headings l, l + 32, ...; then a shuffle reduction
+            for (int k = tid; k < a.A; k += 32) {
+                const unsigned long long eb =
+                    (s_exact != nullptr && k < NVB_STEP_MAX_A_SMEM) ? s_exact[k] : a.exact[(size_t)b * a.A + k];
+                const double fam = __dsub_rn(a.maxfam, __longlong_as_double((long long)eb));
+                if (logging && a.log_afam) a.log_afam[((size_t)t * a.B + b) * a.A + k] = fam;
+                if (best == 0x7FFFFFFF || fam > best_fam) { best = k; best_fam = fam; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double of = __shfl_xor_sync(0xFFFFFFFFu, best_fam, o);
+                const int ok = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+                if (ok != 0x7FFFFFFF && (best == 0x7FFFFFFF || of > best_fam || (of == best_fam && ok < best))) {
+                    best = ok;
+                    best_fam = of;
+                }
+            }
         }
-        const double ang0 = a.ag.poses[3 * b + 2];
-        const double ang = nvb_pymod_pos(__dadd_rn(ang0, a.offsets[best]), NVB_TWO_PI);   // :317
-        double sn, cs;
-        sincos(ang, &sn, &cs);
-        const double x = __dadd_rn(a.ag.poses[3 * b], __dmul_rn(a.step_size, cs));       // :319
-        const double y = __dadd_rn(a.ag.poses[3 * b + 1], __dmul_rn(a.step_size, sn));   // :320
-        a.ag.poses[3 * b] = x;
-        a.ag.poses[3 * b + 1] = y;
-        a.ag.poses[3 * b + 2] = ang;
-        s_pose[0] = x; s_pose[1] = y; s_pose[2] = ang;
-        if (logging) {
-            a.log_best[(size_t)t * a.B + b] = (int16_t)best;
-            a.log_pose[((size_t)t * a.B + b) * 3] = x;
-            a.log_pose[((size_t)t * a.B + b) * 3 + 1] = y;
-            a.log_pose[((size_t)t * a.B + b) * 3 + 2] = ang;
-            a.log_sfam[(size_t)t * a.B + b] = best_fam;
-        }
-        if (a.fake) {
-            a.ag.completed[b] = completed + 1;
-            s_more = (completed + 1 < budget);
+        if (tid == 0) {
+            const double ang = nvb_pymod_pos(__dadd_rn(pre.ang0, offsets[best]), NVB_TWO_PI);   // :317
+            double sn, cs;
+            sincos(ang, &sn, &cs);
+            const double x = __dadd_rn(pre.px, __dmul_rn(a.step_size, cs));   // :319
+            const double y = __dadd_rn(pre.py, __dmul_rn(a.step_size, sn));   // :320
+            s_pose[0] = x; s_pose[1] = y; s_pose[2] = ang;
+            a.ag.poses[3 * b] = x;
+            a.ag.poses[3 * b + 1] = y;
+            a.ag.poses[3 * b + 2] = ang;
+            if (logging) {
+                a.log_best[(size_t)t * a.B + b] = (int16_t)best;
+                a.log_pose[((size_t)t * a.B + b) * 3] = x;
+                a.log_pose[((size_t)t * a.B + b) * 3 + 1] = y;
+                a.log_pose[((size_t)t * a.B + b) * 3 + 2] = ang;
+                a.log_sfam[(size_t)t * a.B + b] = best_fam;
+            }
+            if (a.fake) {
+                a.ag.completed[b] = completed + 1;
+                s_more = (completed + 1 < budget);
+            }
         }
     }
     __syncthreads();
     pose_out[0] = s_pose[0]; pose_out[1] = s_pose[1]; pose_out[2] = s_pose[2];
+    after_pose(pose_out);
+    long long *dbg2 = a.dbg ? a.dbg + (size_t)8 * a.B + (size_t)8 * b : nullptr;
+    if (dbg2 && tid == 0) dbg2[0] = clock64();    // window requested
+    const bool warp1 = W1_HOOK && (tid >> 5) == 1;
+    if (warp1) beside_scan(pose_out);
+    if (dbg2 && tid == 32) dbg2[1] = clock64();   // warp 1 hook done
     if (a.fake) return s_more != 0;
     if (MODE == 1) {
         if (tid == 0) a.dmin2[b] = 0x7FF0000000000000ull;   // +inf: k3_path_scan takes the minimum
@@ -348,36 +404,41 @@ __device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigne
     const double thr2 = a.cover_thr2;
     const bool one_pass = thr <= a.max_dist;
     const double2 *path = reinterpret_cast<const double2 *>(a.path);
+    // the threads that scan: all of them, or all but warp 1 (busy with the hook)
+    const int scan_n = W1_HOOK ? (int)blockDim.x - 32 : (int)blockDim.x;
+    const int scan_id = !W1_HOOK ? tid : warp1 ? a.n_path : (tid < 32 ? tid : tid - 32);
     double m = __longlong_as_double(0x7FF0000000000000ll);
     if (MODE == 2) {
         m = __longlong_as_double((long long)a.dmin2[b]);
     } else {
 #pragma unroll 4
-        for (int n = tid; n < a.n_path; n += NVB_STEP_THREADS) {
+        for (int n = scan_id; n < a.n_path; n += scan_n) {
             const double2 pt = __ldg(path + n);
             const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
             const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
             m = fmin(m, d2);
             if (one_pass && d2 <= thr2) a.ag.coverage[(size_t)b * a.n_path + n] = 1;
         }
+        if (dbg2 && tid == 0) dbg2[2] = clock64();    // warp 0 scanned its share
+        if (dbg2 && tid == 64) dbg2[3] = clock64();   // warp 2 scanned its share
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
         if ((tid & 31) == 0) s_red[tid >> 5] = m;
         __syncthreads();
+        if (dbg2 && tid == 0) dbg2[4] = clock64();    // reduced
         m = s_red[0];
-#pragma unroll
-        for (int wq = 1; wq < NVB_STEP_THREADS / 32; wq++) m = fmin(m, s_red[wq]);
+        for (int wq = 1; wq < (int)(blockDim.x >> 5); wq++) m = fmin(m, s_red[wq]);
     }
     const double dmin = __dsqrt_rn(m);
     if (tid == 0) {
         int go = 1, more = 0;
-        a.ag.nav_frames[b] = nav_frames + 1;                        // :253
+        a.ag.nav_frames[b] = pre.nav_frames + 1;                    // :253
         if (dmin > a.max_dist) {                                    // :263-264
             a.ag.status[b] = -1;
             go = 0;
         } else {
-            a.ag.err_sum[b] = __dadd_rn(err_sum, __dmul_rn(dmin, dmin));   // :267
-            a.ag.err_n[b] = err_n + 1;                                     // :268
+            a.ag.err_sum[b] = __dadd_rn(pre.err_sum, __dmul_rn(dmin, dmin));   // :267
+            a.ag.err_n[b] = pre.err_n + 1;                                     // :268
             // :328 end-of-path test
             const double2 pe = __ldg(path + (a.n_path - 1));
             const double ex = __dsub_rn(pe.x, x), ey = __dsub_rn(pe.y, y);
@@ -391,10 +452,11 @@ __device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigne
         }
         s_go = go;
         s_more = more;
+        if (dbg2) dbg2[5] = clock64();                // bookkeeping done
     }
     __syncthreads();
     if (s_go && !one_pass && dmin <= thr) {                         // :272-276, two-pass form
-        for (int n = tid; n < a.n_path; n += NVB_STEP_THREADS) {
+        for (int n = tid; n < a.n_path; n += blockDim.x) {
             const double2 pt = __ldg(path + n);
             const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
             if (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= thr2)
@@ -453,7 +515,8 @@ k3_step(StepArgs a)
     nvb_decide<true>(a, b, s_exact, s_div);
     __syncthreads();
     double pose[3];
-    nvb_move<0>(a, b, s_exact, pose);
+    const MovePre pre = nvb_move_preload(a, b, s_exact);
+    nvb_move<0>(a, b, s_exact, pre, a.offsets, pose);
 }
 
 // ---- one launch: decide + ties + move of step t, then the glimpses of step t+1 ----
@@ -480,7 +543,8 @@ k31_step_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArg
     __syncthreads();
     if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 2] = clock64();
     double pose[3];
-    const bool more = nvb_move<0>(a, b, s_exact, pose);
+    const MovePre pre = nvb_move_preload(a, b, s_exact);
+    const bool more = nvb_move<0>(a, b, s_exact, pre, a.offsets, pose);
     if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 3] = clock64();
     if (!more) return;
     __syncthreads();
@@ -639,45 +703,85 @@ k3_decide_help(StepArgs a)
         budget -= nvb_tie_sweep(a, s_list[(i + b) % n_list], n_chunks, budget, s_div);
 }
 
+#define NVB_MS_MAX_THREADS 160   /* k3_move_sample runs with 128 or 160 threads (see launch_k3ms_t) */
+
 template <bool NEED_HS, int PH, int PW>
-__global__ void __launch_bounds__(NVB_STEP_THREADS, 8)
+__global__ void __launch_bounds__(NVB_MS_MAX_THREADS, 7)   // 1024 agents = 7 CTAs per SM: one wave
 k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs sa)
 {
+    nvb_tl_stamp(a.tl, 3, 0);
     if (a.pdl_early) nvb_grid_dep_launch();
     extern __shared__ __align__(128) uint8_t smem_k3ms[];
-    // constant data while the tie pass drains: quantisation tables -> shared memory, and the
-    // training path (every CTA of the SM scans all of it) -> L1
-    nvb_sampler_stage_lut(sa.w, nvb_sampler_lut_smem<NEED_HS>(sa.w, sa.A, smem_k3ms));
+    const SamplerSmem L = nvb_sampler_layout<NEED_HS>(sa.w, sa.A, smem_k3ms);
+    // constant data while the tie pass drains: quantisation tables and heading offsets ->
+    // shared memory, the training path (every CTA of the SM scans all of it) -> L1
+    nvb_sampler_stage_lut(sa.w, L.lut);
+    for (int k = threadIdx.x; k < a.A; k += blockDim.x) L.offs[k] = a.offsets[k];
     if (a.n_path <= 4096)
-        for (int o = threadIdx.x * 128; o < a.n_path * 16; o += NVB_STEP_THREADS * 128)
+        for (int o = threadIdx.x * 128; o < a.n_path * 16; o += blockDim.x * 128)
             asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(a.path) + o));
+    if (sa.dbg && threadIdx.x == 0) sa.dbg[blockIdx.x * 8 + 0] = clock64();
+    __syncthreads();
     nvb_grid_dep_wait();
+    nvb_tl_stamp(a.tl, 3, 1);
     const int b = blockIdx.x;
-    if (!a.ag.stepped[b]) {
+    if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 1] = clock64();
+    // everything this agent's move needs, requested before the first branch on any of it
+    const int stepped = a.ag.stepped[b];
+    const MovePre pre = nvb_move_preload(a, b, nullptr);
+    if (!stepped) {
         nvb_log_idle(a, b);
         return;
     }
+    // The window of the NEXT glimpses depends only on the new pose: its TMA loads start as
+    // soon as the pose is known and fly during the path scan of update_error; for sweeps of
+    // up to 32 headings warp 1 computes the rotations meanwhile and the other warps scan.
     double pose[3];
-    const bool more = nvb_move<0>(a, b, nullptr, pose);
-    if (!more) return;
-    __syncthreads();
-    nvb_sample_body<NEED_HS, PH, PW, true>(&tmap, sa, b, pose[0], pose[1], pose[2], smem_k3ms, a.pending_fail + b);
+    bool oob = false;
+    const bool short_sweep = a.A <= 32;
+    auto window = [&](const double *p) {
+        if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 2] = clock64();
+        oob = nvb_sample_window<NEED_HS>(&tmap, sa, b, p[0], p[1], L);
+    };
+    bool more;
+    if (short_sweep) {
+        more = nvb_move<0, true>(a, b, nullptr, pre, L.offs, pose, window,
+                                 [&](const double *p) { nvb_sample_rotations(sa, b, p[2], L, L.offs, 32, 32); });
+    } else {
+        more = nvb_move<0, false>(a, b, nullptr, pre, L.offs, pose, window);
+    }
+    if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 3] = clock64();
+    if (!more) {
+        // the agent stops here; a window in flight must land before the CTA's shared memory goes
+        if (!oob && sa.w.R > 0) nvb_mbar_wait(L.mbar, 0);
+        return;
+    }
+    if (oob) {   // NavBySceneFamiliarity.py:156-158, reported at the step it belongs to
+        if (threadIdx.x == 0) a.pending_fail[b] = -2;
+        return;
+    }
+    if (!short_sweep) nvb_sample_rotations(sa, b, pose[2], L, L.offs, 0, (int)blockDim.x);
+    nvb_sample_gather<NEED_HS, PH, PW>(sa, b, pose[0], pose[1], L, a.pending_fail + b);
+    nvb_tl_stamp(a.tl, 3, 2);
 }
 
 // ---- three launches (large / view-sharded libraries) -----------------------------
 __global__ void __launch_bounds__(NVB_STEP_THREADS, 7)   // 1024 agents = 7 CTAs per SM: one wave
 k3_decide(StepArgs a)
 {
+    nvb_tl_stamp(a.tl, 1, 0);
     if (a.pdl_early) nvb_grid_dep_launch();
     __shared__ double s_div[256];
     for (int k = threadIdx.x; k < 256; k += blockDim.x) s_div[k] = a.div255[k];   // constant table
     nvb_grid_dep_wait();
+    nvb_tl_stamp(a.tl, 1, 1);
     const int b = blockIdx.x;
     nvb_commit_pending(a, b);   // (its barrier also publishes s_div)
     const bool active = nvb_agent_active(a.ag, b);
     if (threadIdx.x == 0) a.ag.stepped[b] = active ? 1 : 0;
     if (!active) return;
     nvb_decide<false>(a, b, nullptr, s_div);
+    nvb_tl_stamp(a.tl, 1, 2);
 }
 
 // Tie pass: every (tied glimpse, local view) pair whose score is within the
@@ -686,9 +790,12 @@ k3_decide(StepArgs a)
 __global__ void __launch_bounds__(NVB_TIE_THREADS)
 k3_ties(StepArgs a)
 {
+    nvb_tl_stamp(a.tl, 2, 0);
     if (a.pdl_early) nvb_grid_dep_launch();
     nvb_grid_dep_wait();
+    nvb_tl_stamp(a.tl, 2, 1);
     const int n_items = *a.tie_count;
+    nvb_tl_stamp(a.tl, 2, 2);   // (overwritten below when there is work)
     if (n_items == 0) return;
     const int chunks = (a.N + NVB_TIE_THREADS - 1) / NVB_TIE_THREADS;
     const long long units = (long long)n_items * chunks;
@@ -704,6 +811,7 @@ k3_ties(StepArgs a)
             atomicMin(a.exact + g, (unsigned long long)__double_as_longlong(d));
         }
     }
+    nvb_tl_stamp(a.tl, 2, 2);
 }
 
 __global__ void __launch_bounds__(NVB_STEP_THREADS)
@@ -717,7 +825,8 @@ k3_move(StepArgs a)
         return;
     }
     double pose[3];
-    nvb_move<0>(a, b, nullptr, pose);
+    const MovePre pre = nvb_move_preload(a, b, nullptr);
+    nvb_move<0>(a, b, nullptr, pre, a.offsets, pose);
 }
 
 
@@ -736,7 +845,8 @@ k3_move_pose(StepArgs a)
         return;
     }
     double pose[3];
-    nvb_move<1>(a, b, nullptr, pose);
+    const MovePre pre = nvb_move_preload(a, b, nullptr);
+    nvb_move<1>(a, b, nullptr, pre, a.offsets, pose);
 }
 
 __global__ void __launch_bounds__(256)
@@ -774,7 +884,8 @@ k3_move_finish(StepArgs a)
     const int b = blockIdx.x;
     if (!a.ag.stepped[b]) return;
     double pose[3];
-    nvb_move<2>(a, b, nullptr, pose);
+    const MovePre pre = nvb_move_preload(a, b, nullptr);
+    nvb_move<2>(a, b, nullptr, pre, a.offsets, pose);
 }
 
 // ---- MIN exchange over NVLink peer memory (view-sharded library, one process per GPU) ----

@@ -10,14 +10,23 @@ eng = NavEngine(L, **kw)
 assert eng.train_from_path(tpath) == (0, -1)
 eng.set_agents(poses)
 eng.step(5); eng.sync()
-out = np.zeros((len(poses), 8), np.int64)
-_cabi.check(eng._lib.nvb_debug_step_clocks(eng._h, _cabi.ptr(out)))
+out2 = np.zeros((2, len(poses), 8), np.int64)
+out = out2[0]
+_cabi.check(eng._lib.nvb_debug_step_clocks(eng._h, _cabi.ptr(out2)))
 ok = out[:, 6] > 0
 d = out[ok]
-names = ["start->active", "active->decided", "decided->moved", "moved->window requested", "requested->landed", "landed->sampled"]
+names = (["start->active", "active->decided", "decided->moved", "moved->window requested", "requested->landed", "landed->sampled"]
+         if os.environ.get("NAVSIM_B200_STEP_FORM") == "1" else
+         ["resident->dependency met", "dependency met->pose", "pose->moved (scan, bookkeeping, rotations)", "moved->gather entered", "entered->window landed", "landed->sampled"])
 for i, n in enumerate(names):
     x = (d[:, i + 1] - d[:, i]) / 1.965e3
     print("%-26s mean %6.2f us  p10 %6.2f  p90 %6.2f" % (n, x.mean(), np.percentile(x, 10), np.percentile(x, 90)))
+if os.environ.get("NAVSIM_B200_STEP_FORM") != "1":
+    f = out2[1][ok]
+    base = d[:, 2]   # pose published
+    for i, n in enumerate(["window requested", "warp 1 hook done", "warp 0 scanned", "warp 2 scanned", "reduced", "bookkeeping done"]):
+        x = (f[:, i] - base) / 1.965e3
+        print("   pose -> %-20s mean %6.2f us  p10 %6.2f  p90 %6.2f" % (n, x.mean(), np.percentile(x, 10), np.percentile(x, 90)))
 tot = (d[:, 6] - d[:, 0]) / 1.965e3
 print("total per CTA  mean %.2f us  max %.2f us   (n=%d)" % (tot.mean(), tot.max(), len(d)))
 order = np.argsort(-tot)[:8]
