@@ -544,8 +544,15 @@ static int launch_dist_cpr(nvb_engine *e, const DistArgs &da)
     // many glimpses: 64-glimpse x 240- or 256-view tiles (4 x 15|16 sums per thread);
     // the width that wastes fewer padded views wins
     const long long pad15 = ((da.N + 239) / 240) * 240LL, pad16 = ((da.N + 255) / 256) * 256LL;
-    static const int mg = getenv("NAVSIM_B200_K2_MG") ? atoi(getenv("NAVSIM_B200_K2_MG")) : 4;
-    if (mg == 3) {   // tuning knob: 48-glimpse tiles (finer SM-level balance)
+    // 64- or 48-glimpse tiles: whichever leaves the busiest SM with less to do (tiles are
+    // dealt out whole; the smaller tile pays ~2 % in shared-memory traffic per comparison).
+    // C2 (10240 glimpses x 6 view tiles on 148 SMs): 7 x 64 vs 9 x 48 rows -> 48.
+    static const int forced_mg = getenv("NAVSIM_B200_K2_MG") ? atoi(getenv("NAVSIM_B200_K2_MG")) : 0;
+    const long long n_vt = (pad15 < pad16 ? pad15 / 240 : pad16 / 256), sms = e->sm_count;
+    const long long busiest4 = ((((da.G + 63) / 64) * n_vt + sms - 1) / sms) * 64;
+    const long long busiest3 = ((((da.G + 47) / 48) * n_vt + sms - 1) / sms) * 48;
+    const int mg = forced_mg ? forced_mg : (busiest3 * 102 < busiest4 * 100 ? 3 : 4);
+    if (mg == 3) {
         if (pad15 < pad16) return launch_dist_cfg<16, 3, 15, CPR>(e, da);
         return launch_dist_cfg<16, 3, 16, CPR>(e, da);
     }

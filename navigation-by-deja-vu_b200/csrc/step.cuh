@@ -776,9 +776,26 @@ k3_decide(StepArgs a)
     nvb_grid_dep_wait();
     nvb_tl_stamp(a.tl, 1, 1);
     const int b = blockIdx.x;
-    nvb_commit_pending(a, b);   // (its barrier also publishes s_div)
-    const bool active = nvb_agent_active(a.ag, b);
-    if (threadIdx.x == 0) a.ag.stepped[b] = active ? 1 : 0;
+    // everything the first decisions need, requested in one round trip; thread 0 alone
+    // decides whether the agent takes part (the others must not race its status update)
+    __shared__ int s_active;
+    if (threadIdx.x < a.A && threadIdx.x < 32)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.keys + (size_t)b * a.A + threadIdx.x));
+    if (threadIdx.x == 0) {
+        const int pf = (a.pending_fail != nullptr) ? a.pending_fail[b] : 0;
+        const int status = a.ag.status[b], completed = a.ag.completed[b], budget = a.ag.budget[b];
+        // a failure the sampler found for THIS step while it ran at the end of the previous
+        // one becomes the agent's status now (as nvb_commit_pending)
+        if (pf != 0) {
+            a.ag.status[b] = pf;
+            a.pending_fail[b] = 0;
+        }
+        const int active = (pf == 0) && status == 0 && completed < budget;
+        a.ag.stepped[b] = active;
+        s_active = active;
+    }
+    __syncthreads();   // s_active, s_div
+    const bool active = s_active != 0;
     if (!active) return;
     nvb_decide<false>(a, b, nullptr, s_div);
     nvb_tl_stamp(a.tl, 1, 2);
@@ -794,15 +811,20 @@ k3_ties(StepArgs a)
     if (a.pdl_early) nvb_grid_dep_launch();
     nvb_grid_dep_wait();
     nvb_tl_stamp(a.tl, 2, 1);
+    const int chunks = (a.N + NVB_TIE_THREADS - 1) / NVB_TIE_THREADS;
+    // the list entry this CTA would start with is requested together with the list length
+    // (one round trip instead of two; the list arrays hold at least B * A entries)
+    const int item0 = min((int)(blockIdx.x / chunks), a.B * a.A - 1);
+    const int g0 = a.tie_items[item0].x;
+    const unsigned long long thr0 = a.tie_thr[item0];
     const int n_items = *a.tie_count;
     nvb_tl_stamp(a.tl, 2, 2);   // (overwritten below when there is work)
     if (n_items == 0) return;
-    const int chunks = (a.N + NVB_TIE_THREADS - 1) / NVB_TIE_THREADS;
     const long long units = (long long)n_items * chunks;
     for (long long u = blockIdx.x; u < units; u += gridDim.x) {
         const int item = (int)(u / chunks), ch = (int)(u - (long long)item * chunks);
-        const int g = a.tie_items[item].x;
-        const unsigned long long thr = a.tie_thr[item];
+        const int g = (u == blockIdx.x) ? g0 : a.tie_items[item].x;
+        const unsigned long long thr = (u == blockIdx.x) ? thr0 : a.tie_thr[item];
         const int v = ch * NVB_TIE_THREADS + threadIdx.x;
         if (v >= a.N) continue;
         const size_t qo = (size_t)g * a.Ppad, fo = (size_t)v * a.Ppad;
