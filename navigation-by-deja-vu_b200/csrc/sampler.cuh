@@ -32,12 +32,14 @@ struct SamplerArgs {
 };
 
 #define NVB_SAMPLER_THREADS 256
+#define NVB_PTAB_MAX 256   /* sensors of up to this many pixels keep a per-pixel origin table in shared memory */
 
 // Host + device: dynamic shared memory of k1_sample.
 __host__ __device__ inline size_t nvb_sampler_smem(int BW, int BH, int nplanes, int A)
 {
     size_t win = (size_t)nvb_round_up(BW * BH, 128) * (size_t)nplanes;
-    return win + (size_t)A * 32 + 64 + 768;   // + rotations (FP64 and FP32), heading offsets, mbarrier, tables
+    // + rotations (FP64 and FP32), heading offsets, mbarrier, quantisation tables, pixel table
+    return win + (size_t)A * 32 + 64 + 768 + NVB_PTAB_MAX * 8;
 }
 
 // Sample coordinates (util.pyx:159-168).  The reference evaluates
@@ -152,6 +154,17 @@ __device__ __forceinline__ void nvb_sampler_stage_lut(const NvbWorld &w, uint8_t
     for (int k = threadIdx.x; k < 768 / 4; k += blockDim.x)
         reinterpret_cast<uint32_t *>(lut_sm)[k] = __ldg(reinterpret_cast<const uint32_t *>(w.lut) + k);
 }
+// Sensor pixel p = bi * W + bj -> sensor-frame coordinates of its block's first sample
+// (util.pyx:159-160: col - Wpx/2, row - Hpx/2; halves are exact in FP32).  Constant per world.
+__device__ __forceinline__ void nvb_sampler_stage_ptab(const NvbWorld &w, float2 *ptab)
+{
+    if (w.P > NVB_PTAB_MAX) return;
+    const float half_wf = 0.5f * (float)w.Wpx, half_hf = 0.5f * (float)w.Hpx;
+    for (int p = threadIdx.x; p < w.P; p += blockDim.x) {
+        const int bi = p / w.W, bj = p - bi * w.W;
+        ptab[p] = make_float2((float)(bj * w.pw) - half_wf, (float)(bi * w.ph) - half_hf);
+    }
+}
 
 // Shared-memory layout of one sampling CTA (dynamic shared memory, nvb_sampler_smem bytes).
 struct SamplerSmem {
@@ -161,6 +174,7 @@ struct SamplerSmem {
     uint8_t *lut;                     // [3][256] quantisation tables
     float2 *csf;                      // [A] the rotations rounded to FP32 (fast path)
     double *offs;                     // [A] heading offsets (staged by kernels that want them close)
+    float2 *ptab;                     // [P <= NVB_PTAB_MAX] sensor pixel -> (px0, py0), its block's origin
     int *err;                         // IndexError flag of this CTA
 };
 
@@ -178,7 +192,8 @@ __device__ __forceinline__ SamplerSmem nvb_sampler_layout(const NvbWorld &w, int
     L.lut = (uint8_t *)(L.mbar + 1);
     L.csf = (float2 *)(L.lut + 768);
     L.offs = (double *)(L.csf + A);
-    L.err = (int *)(L.offs + A);
+    L.ptab = (float2 *)(L.offs + A);
+    L.err = (int *)(L.ptab + NVB_PTAB_MAX);
     return L;
 }
 
@@ -258,7 +273,10 @@ __device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const S
         return;
     }
     // while the window is in flight: quantisation tables -> shared memory, rotations
-    if (!LUT_STAGED) nvb_sampler_stage_lut(a.w, L.lut);
+    if (!LUT_STAGED) {
+        nvb_sampler_stage_lut(a.w, L.lut);
+        nvb_sampler_stage_ptab(a.w, L.ptab);
+    }
     nvb_sample_rotations(a, b, ang, L, a.offsets, 0, (int)blockDim.x);
     nvb_sample_gather<NEED_HS, PH, PW>(a, b, x, y, L, fail_out);
 }
@@ -304,17 +322,32 @@ __device__ __forceinline__ void nvb_sample_gather(const SamplerArgs &a, int b, d
     // window index of sample (lx, ly) relative to (floor x, floor y), with the magic-number
     // bias of both float bit patterns folded in (32-bit wrap-around arithmetic is exact)
     const int kbase = ((yi - oy) - NVB_RND_MAGIC_BITS) * w.BW + ((xi - ox) - NVB_RND_MAGIC_BITS);
-    const float inv_p = 1.0f / (float)w.P, inv_w = 1.0f / (float)w.W;
+    const float inv_w = 1.0f / (float)w.W;
     const float half_wf = (float)c.q.half_w, half_hf = (float)c.q.half_h;
     int err = 0;
 
-    for (int it = tid; it < a.A * w.P; it += blockDim.x) {
-        // it = k * P + bi * W + bj  (small integers: the float quotients are exact)
-        const int k = (int)(((float)it + 0.5f) * inv_p), p = it - k * w.P;
-        const int bi = (int)(((float)p + 0.5f) * inv_w), bj = p - bi * w.W;
+    // it = k * P + p, p = bi * W + bj: k and p advance incrementally (no divisions in the loop)
+    const int T = (int)blockDim.x;
+    const int dk = T / w.P, dp = T - dk * w.P;
+    int k = tid / w.P, p = tid - k * w.P;
+    const bool have_tab = w.P <= NVB_PTAB_MAX;
+    const bool linear_out = (w.Ppad == w.P);   // then the output offset of item `it` is just `it`
+    // NavBySceneFamiliarity.py:189-190 in units of px0 = bj * pw - Wpx / 2 (exact in FP32)
+    const float mask_lo = (float)(w.mask_lo * pw) - half_wf, mask_hi = (float)(w.mask_hi * pw) - half_wf;
+    const size_t out0 = (size_t)b * a.A * w.Ppad;
+
+    for (int it = tid; it < a.A * w.P; it += T) {
+        float px0, py0;
+        if (have_tab) {
+            const float2 e = L.ptab[p];
+            px0 = e.x; py0 = e.y;
+        } else {
+            // small integers: the float quotient is exact
+            const int bi = (int)(((float)p + 0.5f) * inv_w), bj = p - bi * w.W;
+            px0 = (float)(bj * pw) - half_wf; py0 = (float)(bi * ph) - half_hf;
+        }
         const float2 csf = csf_sm[k];
         const float cf = csf.x, sf = csf.y;
-        const int row0 = bi * ph, col0 = bj * pw;
         int sum_v = 0, n = 0;
         uint8_t hh[NEED_HS ? NVB_MAX_BLOCK_PX : 1], ss[NEED_HS ? NVB_MAX_BLOCK_PX : 1];
         bool done = false;
@@ -322,7 +355,6 @@ __device__ __forceinline__ void nvb_sample_gather(const SamplerArgs &a, int b, d
             // lean path: no branches; the largest distance from a rounding tie seen in
             // the block decides afterwards whether it must be redone
             // (sm_100 packed FP32x2: x and y coordinate advance, round and compare together)
-            const float px0 = (float)col0 - half_wf, py0 = (float)row0 - half_hf;
             const float2 t_row0 = make_float2(fmaf(px0, cf, fmaf(-py0, sf, c.xf)), fmaf(px0, sf, fmaf(py0, cf, c.yf)));
             float2 t_row = t_row0;
             const float2 step_j = make_float2(cf, sf), step_i = make_float2(-sf, cf);
@@ -348,6 +380,7 @@ __device__ __forceinline__ void nvb_sample_gather(const SamplerArgs &a, int b, d
                 // re-addressed with the reference's FP64 expression and the sum corrected.
                 if (a.dbg) atomicAdd((unsigned long long *)a.dbg + b * 8 + 7, 1ull);
                 c.q.c = cs_sm[2 * k]; c.q.s = cs_sm[2 * k + 1];
+                const int col0 = (int)(px0 + half_wf), row0 = (int)(py0 + half_hf);
                 t_row = t_row0;
 #pragma unroll
                 for (int i = 0; i < ph; i++) {
@@ -373,14 +406,15 @@ __device__ __forceinline__ void nvb_sample_gather(const SamplerArgs &a, int b, d
         }
         if (!done) {
             c.q.c = cs_sm[2 * k]; c.q.s = cs_sm[2 * k + 1];
+            const int col0 = (int)(px0 + half_wf), row0 = (int)(py0 + half_hf);
             sum_v = nvb_block_careful<NEED_HS>(c, cf, sf, col0, row0, hh, ss, &n, &err);
         }
         // util.pyx:121-123: V = (uint8) round(sum / (fr*fc)), half away from zero.  In
         // integers: the quotient is either an exact tie or at least 1/(2*fr*fc) away
         // from one, far more than the FP64 division's rounding.
         uint8_t v = (uint8_t)((2 * sum_v + nblk) / (2 * nblk));
-        const bool masked = (bj >= w.mask_lo && bj < w.mask_hi);   // NavBySceneFamiliarity.py:189-190
-        const size_t o = ((size_t)b * a.A + k) * w.Ppad + p;
+        const bool masked = (px0 >= mask_lo && px0 < mask_hi);
+        const size_t o = out0 + (linear_out ? (size_t)it : (size_t)k * w.Ppad + p);
         a.gv[o] = masked ? 0 : lut_sm[512 + v];
         if (NEED_HS) {
             // util.pyx:126-132: hue with the largest summed S (strict >, so the
@@ -402,6 +436,9 @@ __device__ __forceinline__ void nvb_sample_gather(const SamplerArgs &a, int b, d
             a.gh[o] = masked ? 0 : lut_sm[best_h];
             a.gs[o] = masked ? 0 : lut_sm[256 + sat];
         }
+        k += dk;
+        p += dp;
+        if (p >= w.P) { p -= w.P; k++; }
     }
     if (err) *L.err = 1;
     __syncthreads();

@@ -716,6 +716,7 @@ k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs
     // constant data while the tie pass drains: quantisation tables and heading offsets ->
     // shared memory, the training path (every CTA of the SM scans all of it) -> L1
     nvb_sampler_stage_lut(sa.w, L.lut);
+    nvb_sampler_stage_ptab(sa.w, L.ptab);
     for (int k = threadIdx.x; k < a.A; k += blockDim.x) L.offs[k] = a.offsets[k];
     if (a.n_path <= 4096)
         for (int o = threadIdx.x * 128; o < a.n_path * 16; o += blockDim.x * 128)
