@@ -125,8 +125,24 @@ __device__ __forceinline__ unsigned long long nvb_pair_score(const StepArgs &a, 
     const uint32_t *qv = reinterpret_cast<const uint32_t *>(a.gv + qo);
     const uint32_t *fv = reinterpret_cast<const uint32_t *>(a.lv + fo);
     if (a.cw == 0.0) {
+        // rows are 16-byte aligned and zero padded: 16-byte loads, up to five chunks of both
+        // rows (an 80-pixel sensor) in flight at once
+        const uint4 *q4 = reinterpret_cast<const uint4 *>(qv);
+        const uint4 *f4 = reinterpret_cast<const uint4 *>(fv);
+        const int nc = a.Ppad / 16;
         uint32_t s = 0;
-        for (int wd = 0; wd < words; wd++) s = nvb_sad4(qv[wd], __ldg(fv + wd), s);
+        for (int c0 = 0; c0 < nc; c0 += 5) {
+            uint4 qq[5], ff[5];
+#pragma unroll
+            for (int u = 0; u < 5; u++)
+                if (c0 + u < nc) { qq[u] = q4[c0 + u]; ff[u] = __ldg(f4 + c0 + u); }
+#pragma unroll
+            for (int u = 0; u < 5; u++)
+                if (c0 + u < nc) {
+                    s = nvb_sad4(qq[u].x, ff[u].x, s); s = nvb_sad4(qq[u].y, ff[u].y, s);
+                    s = nvb_sad4(qq[u].z, ff[u].z, s); s = nvb_sad4(qq[u].w, ff[u].w, s);
+                }
+        }
         return s;
     }
     const uint32_t *qh = reinterpret_cast<const uint32_t *>(a.gh + qo);
