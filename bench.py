@@ -224,6 +224,13 @@ def run_ours(args):
     k2_ms, k2_n = eng.kernel_time_ms()
     eng.set_options(use_graph=True, kernel_timing=False)
     k2_alone_ms = eng.time_distance_kernel(20)
+    # the same kernel inside the replayed step graph: first CTA resident -> last CTA done,
+    # stamped with the global timer by the kernel itself (supplementary; events cannot be
+    # placed inside the graph without breaking the programmatic launch overlap they measure)
+    eng.rewind()
+    tl = eng.timeline(8)
+    k2_graph_ms = (tl["k2_sad_v"][2] - tl["k2_sad_v"][0]) * 1e-3 if "k2_sad_v" in tl else None
+    eng.rewind()
     sad_peak = eng.probe_sad_peak(8192)           # pixel-compares / s, register resident
 
     # ---- e2e: per step pinned host poses in, results out, one sync
@@ -272,6 +279,10 @@ def run_ours(args):
         "peak_source": "VABSDIFF4.U8.ACC issue-rate probe measured in this run (nvb_probe_sad_peak); "
                        "not in MEASURED_PEAKS.json",
         "launch_ms": k2_s * 1e3, "launch_ms_alone": k2_alone_ms, "launches_timed": k2_n,
+        "launch_ms_in_graph": k2_graph_ms,
+        "frac_in_graph": (ops / (k2_graph_ms * 1e-3)) / (2.0 * sad_peak) if k2_graph_ms else None,
+        "step_timeline_us": {k: [round(x, 2) for x in v] if isinstance(v, tuple) else round(v, 2)
+                             for k, v in tl.items()},
         "hbm_achieved_gbs": alg_bytes / k2_s / 1e9, "hbm_peak_gbs": hbm_peak,
         "hbm_frac": alg_bytes / k2_s / 1e9 / hbm_peak,
         "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",

@@ -342,6 +342,29 @@ class NavEngine(object):
     def time_distance_kernel(self, reps=20):
         return float(self._lib.nvb_time_distance_kernel(self._h, int(reps)))
 
+    def timeline(self, nsteps=8):
+        """Tuning aid: runs `nsteps` step-batches as step() does and returns, for the last one,
+        {kernel: (first CTA resident, first dependency met, last CTA done)} in microseconds
+        since the step-batch's first stamp, plus 'span' = the whole step-batch."""
+        out = np.zeros((4, 2048, 3), np.int64)
+        check(self._lib.nvb_debug_timeline(self._h, int(nsteps), ptr(out)))
+        names = ["k2_sad_v", "k3_decide", "k3_ties", "k3_move_sample"]
+        res = {}
+        t0 = None
+        for k, name in enumerate(names):
+            d = out[k]
+            ok = d[:, 0] > 0
+            if not ok.any():
+                continue
+            done = d[ok][:, 2]
+            done = done[done > 0]
+            res[name] = (int(d[ok][:, 0].min()), int(d[ok][:, 1].min()), int(done.max()) if len(done) else 0)
+            t0 = res[name][0] if t0 is None else min(t0, res[name][0])
+        out_us = {k: tuple((x - t0) / 1e3 for x in v) for k, v in res.items()}
+        if out_us:
+            out_us["span"] = max(v[2] for v in out_us.values())
+        return out_us
+
     def device_ptr(self, which):
         return self._lib.nvb_device_ptr(self._h, int(which))
 
