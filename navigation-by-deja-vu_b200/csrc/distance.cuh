@@ -31,7 +31,7 @@ struct DistArgs {
     int n_vt, vt_per_split;       // view tiles (and, for the HSV kernel, tiles per blockIdx.y)
     const int *spans;             // [gridDim.x + 1] unit boundaries per CTA (k2_sad_v)
     int *step_counter;            // resident loop: device step index, bumped once per launch; else nullptr
-    int *tie_count;               // resident loop: tie work list length, reset per launch
+    int *tie_count;               // resident loop: [0] tie work list length, [1] units done; reset per launch
     long long view_offset;        // global index of local view 0 (library shards)
     unsigned long long *keys;     // [G], pre-set to ~0
     double cw;
@@ -149,7 +149,8 @@ k2_sad_v(DistArgs a)
         // one step-batch = one launch of this kernel: next log slot, empty tie list
         // (the kernels that read them run after this one)
         *a.step_counter += 1;
-        *a.tie_count = 0;
+        a.tie_count[0] = 0;   // list length
+        a.tie_count[1] = 0;   // tie units completed (tie pass folded into move+sample)
     }
     if (total <= 0) return;
 
@@ -357,7 +358,8 @@ k2_sad_hsv(DistArgs a)
     nvb_grid_dep_wait();
     if (a.step_counter != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
         *a.step_counter += 1;
-        *a.tie_count = 0;
+        a.tie_count[0] = 0;   // list length
+        a.tie_count[1] = 0;   // tie units completed (tie pass folded into move+sample)
     }
     const int words = a.Ppad / 4;
     uint32_t *sm = reinterpret_cast<uint32_t *>(smem);

@@ -102,6 +102,7 @@ struct nvb_engine {
     unsigned long long *d_dmin2 = nullptr;   // [B] long-path form of update_error
     long long *d_dbg = nullptr;     // tuning aid: per-agent clock64 checkpoints of one step
     long long *d_tl = nullptr;      // tuning aid: per-CTA wall-clock stamps of the step kernels
+    int ms_capacity = -1;           // CTAs of k3_move_sample the device holds at once (form 4 needs B <= this)
     int32_t *d_pending = nullptr;   // [B] sampler failure parked for the next step (fused loop)
     bool glimpses_pending = false;  // the glimpses of the next step are already sampled
     double *d_poses0 = nullptr;     // start poses / budgets kept for nvb_agents_rewind
@@ -129,14 +130,18 @@ struct nvb_engine {
     double *log_pose = nullptr, *log_sfam = nullptr, *log_afam = nullptr;
 };
 
-// Step form for small un-sharded libraries, NAVSIM_B200_STEP_FORM (measured warm on C2):
-//   3 (default)  K2 | decide | grid-wide tie pass | move + sample      62 us / step-batch
-//   1            K2 | decide + ties + move + sample in one launch      69 us (tie agents set the tail)
-//   2            K2 | decide + cooperative ties | move + sample        78 us
+// Step form for small un-sharded libraries, NAVSIM_B200_STEP_FORM (C2, warm, us per step-batch):
+//   3 (default)  K2 | decide | grid-wide tie pass | move + sample                          50.6
+//   4            K2 | decide | move + sample with the tie pass folded into its front       52.3
+//                (needs the whole move+sample grid co-resident, else form 3 is used; the agents
+//                with ties are the critical path either way, so only a launch boundary is saved
+//                and the extra code in the big kernel costs more)
+//   1            K2 | decide + ties + move + sample in one launch      (tie agents set the tail)
+//   2            K2 | decide + cooperative ties | move + sample
 static int step_form()
 {
     static const int v = getenv("NAVSIM_B200_STEP_FORM") ? atoi(getenv("NAVSIM_B200_STEP_FORM")) : 3;
-    return (v >= 1 && v <= 3) ? v : 3;
+    return (v >= 1 && v <= 4) ? v : 3;
 }
 
 static bool split_step() { return step_form() != 1; }
@@ -302,7 +307,7 @@ extern "C" int nvb_engine_create(int device, void *stream, nvb_engine **out)
     if (rc) { delete e; return rc; }
     cudaMemcpy(e->d_div255, div, sizeof div, cudaMemcpyHostToDevice);
     alloc_dev(&e->d_step, 1);
-    alloc_dev(&e->d_tie_count, 1);
+    alloc_dev(&e->d_tie_count, 2);   // [0] list length, [1] tie units done (step form 4)
     alloc_dev(&e->d_lut, 768);
     *out = e;
     return NVB_OK;
@@ -410,6 +415,7 @@ extern "C" int nvb_set_saccade(nvb_engine *e, int A, const double *offs)
     CK(cudaMemcpy(e->d_offsets, offs, sizeof(double) * A, cudaMemcpyHostToDevice));
     e->A = A;
     e->B = 0;
+    e->ms_capacity = -1;
     return rebuild_tmap(e);
 }
 
@@ -779,6 +785,7 @@ extern "C" int nvb_library_build(nvb_engine *e, const double *path, const double
             return st[i];
         }
     e->B = 0;
+    e->ms_capacity = -1;
     return set_path(e, path, N);
 }
 
@@ -801,6 +808,7 @@ extern "C" int nvb_library_upload(nvb_engine *e, const uint8_t *scenes, const do
     CK(cudaStreamSynchronize(e->stream));
     cudaFree(d_in);
     e->B = 0;
+    e->ms_capacity = -1;
     if (path) return set_path(e, path, N);
     e->n_path = 0;
     return NVB_OK;
@@ -813,6 +821,7 @@ extern "C" int nvb_set_training_path(nvb_engine *e, const double *path, int n)
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
     e->B = 0;   // coverage is sized by the path
+    e->ms_capacity = -1;
     return set_path(e, path, n);
 }
 
@@ -990,7 +999,7 @@ extern "C" int nvb_agents_set(nvb_engine *e, const double *poses, const int32_t 
     CK(cudaMemsetAsync(e->d_pending, 0, sizeof(int32_t) * B, e->stream));
     CK(cudaMemsetAsync(e->d_tie_ready, 0, sizeof(int) * (size_t)B * e->A, e->stream));   // epochs restart
     e->glimpses_pending = false;
-    CK(cudaMemsetAsync(e->d_tie_count, 0, sizeof(int), e->stream));
+    CK(cudaMemsetAsync(e->d_tie_count, 0, 2 * sizeof(int), e->stream));
     e->steps_done = 0;
     CK(cudaStreamSynchronize(e->stream));
     return NVB_OK;
@@ -1081,16 +1090,37 @@ static int launch_k31_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa,
     return NVB_OK;
 }
 
+// The form actually run for this engine: form 4 only while every CTA of move+sample (one per
+// agent) is resident at once -- its tie agents wait for work done by the other CTAs.
+static int effective_form(const nvb_engine *e)
+{
+    const int f = step_form();
+    if (f == 4 && e->ms_capacity >= 0 && e->B > e->ms_capacity) return 3;
+    return f;
+}
+
 template <bool HS, int PH, int PW>
 static int launch_k3ms_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa, size_t smem)
 {
     static size_t attr_set[64] = {0};
     size_t &cur = attr_set[e->device & 63];
     if (smem > cur) {
-        CK(cudaFuncSetAttribute(k3_move_sample<HS, PH, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k3_move_sample<HS, PH, PW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k3_move_sample<HS, PH, PW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
     }
-    const bool three = step_form() == 3;
+    // 128 or 160 threads, whichever leaves fewer idle lanes in the gather loop over the
+    // A * P sensor pixels (the default 10 x 80 = 800 is exactly five passes of 160)
+    const long long items = (long long)e->A * e->P;
+    const long long w128 = ((items + 127) / 128) * 128, w160 = ((items + 159) / 160) * 160;
+    static const int forced = getenv("NAVSIM_B200_MS_THREADS") ? atoi(getenv("NAVSIM_B200_MS_THREADS")) : 0;
+    const int threads = forced ? forced : (w160 < w128 ? NVB_MS_MAX_THREADS : NVB_STEP_THREADS);
+    if (e->ms_capacity < 0) {
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_move_sample<HS, PH, PW, true>, threads, smem));
+        e->ms_capacity = occ * e->sm_count;
+    }
+    const int form = effective_form(e);
     cudaEvent_t *tev = nullptr;
     if (e->timing && getenv("NAVSIM_B200_TIME_ALL")) {   // tuning aid: events around every kernel
         if (e->ev3.size() < e->ev3_used + 4) {
@@ -1100,22 +1130,21 @@ static int launch_k3ms_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa
         e->ev3_used += 4;
         cudaEventRecord(tev[0], e->stream);
     }
-    if (three) {   // decide | grid-wide tie pass | move + sample
+    if (form >= 3) {   // decide | [grid-wide tie pass |] move + sample
         CK(launch_seq(k3_decide, dim3(e->B), dim3(NVB_STEP_THREADS), 0, e->stream, s));
         if (tev) cudaEventRecord(tev[1], e->stream);
-        CK(launch_seq(k3_ties, dim3(e->sm_count * 2), dim3(NVB_TIE_THREADS), 0, e->stream, s));
+        if (form == 3) {
+            CK(launch_seq(k3_ties, dim3(e->sm_count * 2), dim3(NVB_TIE_THREADS), 0, e->stream, s));
+            e->launches += 1;
+        }
         if (tev) cudaEventRecord(tev[2], e->stream);
-        e->launches += 1;
     } else {
         k3_decide_help<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
     }
-    // 128 or 160 threads, whichever leaves fewer idle lanes in the gather loop over the
-    // A * P sensor pixels (the default 10 x 80 = 800 is exactly five passes of 160)
-    const long long items = (long long)e->A * e->P;
-    const long long w128 = ((items + 127) / 128) * 128, w160 = ((items + 159) / 160) * 160;
-    static const int forced = getenv("NAVSIM_B200_MS_THREADS") ? atoi(getenv("NAVSIM_B200_MS_THREADS")) : 0;
-    const int threads = forced ? forced : (w160 < w128 ? NVB_MS_MAX_THREADS : NVB_STEP_THREADS);
-    CK(launch_seq(k3_move_sample<HS, PH, PW>, dim3(e->B), dim3(threads), smem, e->stream, e->tmap, s, sa));
+    if (form == 4)
+        CK(launch_seq(k3_move_sample<HS, PH, PW, true>, dim3(e->B), dim3(threads), smem, e->stream, e->tmap, s, sa));
+    else
+        CK(launch_seq(k3_move_sample<HS, PH, PW, false>, dim3(e->B), dim3(threads), smem, e->stream, e->tmap, s, sa));
     if (tev) cudaEventRecord(tev[3], e->stream);
     e->launches += 2;
     CK(cudaGetLastError());
@@ -1239,7 +1268,7 @@ static int one_step(nvb_engine *e, const StepArgs &s, bool sample_next = true)
             e->glimpses_pending = true;
             return NVB_OK;
         }
-        if (step_form() == 3) {   // decide | grid-wide tie pass | move, nothing sampled ahead
+        if (step_form() >= 3) {   // decide | grid-wide tie pass | move, nothing sampled ahead
             CK(launch_seq(k3_decide, dim3(e->B), dim3(NVB_STEP_THREADS), 0, e->stream, s));
             CK(launch_seq(k3_ties, dim3(e->sm_count * 2), dim3(NVB_TIE_THREADS), 0, e->stream, s));
             CK(launch_seq(k3_move, dim3(e->B), dim3(NVB_STEP_THREADS), 0, e->stream, s));
@@ -1311,7 +1340,8 @@ static int run_steps(nvb_engine *e, int nsteps, int fake, int log_afam, bool eag
         }
         // launches per step-batch: K2, decide, ties, move+sample | K1, K2, decide, ties, move
         // (+2 for the long-path move, +2 for the NVLink exchanges)
-        const int per_step = fused_step(e) ? (step_form() == 3 ? 4 : step_form() == 2 ? 3 : 2)
+        const int ef = effective_form(e);
+        const int per_step = fused_step(e) ? (ef == 3 ? 4 : (ef == 2 || ef == 4) ? 3 : 2)
                                            : 5 + (e->n_path > NVB_PATH_SPLIT && !fake ? 2 : 0) + (e->p2p_on ? 2 : 0);
         for (int i = done; i < nsteps; i++) {
             CK(cudaGraphLaunch(e->graph_exec, e->stream));
@@ -1397,7 +1427,7 @@ extern "C" int nvb_agents_step_io(nvb_engine *e, const double *poses_in, int nst
             e->graph_dirty = false;
         } else {
             CK(cudaGraphLaunch(e->graph_io, e->stream));
-            e->launches += fused_step(e) && step_form() != 3 ? 3 : 5;
+            e->launches += fused_step(e) && step_form() < 3 ? 3 : 5;
             e->steps_done += 1;
         }
     } else if ((rc = run_steps(e, nsteps, 0, 0, poses_in != nullptr))) {

@@ -199,6 +199,7 @@ __device__ __forceinline__ void nvb_decide(const StepArgs &a, int b, unsigned lo
     }
     thr = s_min + a.band;
     have_ties = s_ntied > 1;
+    if (!FUSED && have_ties && tid == 0) a.ag.stepped[b] = 2;   // takes part AND waits for the tie pass
     for (int k = tid; k < a.A; k += blockDim.x) {
         const size_t g = (size_t)b * a.A + k;
         const unsigned long long key = a.keys[g];
@@ -357,8 +358,9 @@ __device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigne
         } else {
             // warp 0: lane l looks at headings l, l + 32, ...; then a shuffle reduction
             for (int k = tid; k < a.A; k += 32) {
-                const unsigned long long eb =
-                    (s_exact != nullptr && k < NVB_STEP_MAX_A_SMEM) ? s_exact[k] : a.exact[(size_t)b * a.A + k];
+                // (ld.cg: other SMs may have lowered these with atomicMin during this kernel)
+                const unsigned long long eb = (s_exact != nullptr && k < NVB_STEP_MAX_A_SMEM)
+                                                  ? s_exact[k] : __ldcg(a.exact + (size_t)b * a.A + k);
                 const double fam = __dsub_rn(a.maxfam, __longlong_as_double((long long)eb));
                 if (logging && a.log_afam) a.log_afam[((size_t)t * a.B + b) * a.A + k] = fam;
                 if (best == 0x7FFFFFFF || fam > best_fam) { best = k; best_fam = fam; }
@@ -721,7 +723,96 @@ k3_decide_help(StepArgs a)
 
 #define NVB_MS_MAX_THREADS 160   /* k3_move_sample runs with 128 or 160 threads (see launch_k3ms_t) */
 
-template <bool NEED_HS, int PH, int PW>
+// ---- the tie pass folded into move+sample (TIES) ---------------------------------------
+// k3_decide has listed every (tied heading) item.  Every CTA of move+sample first scores its
+// share of the (item, view chunk) units -- unit u belongs to CTA u mod gridDim -- and adds
+// the number it did to tie_count[1]; only the agents that HAVE ties wait until every unit is
+// done.  Nobody waits before finishing its own share, and the engine uses this form only
+// when the whole grid is co-resident, so the wait is short; should it ever last too long
+// (another engine's kernels holding SM slots) the waiting CTA scans its own items alone:
+// atomicMin is idempotent, the result is the same.
+__device__ __forceinline__ void nvb_tie_unit(const StepArgs &a, int g, unsigned long long thr, int v)
+{
+    if (v >= a.N) return;
+    const size_t qo = (size_t)g * a.Ppad, fo = (size_t)v * a.Ppad;
+    unsigned long long score;
+    if (a.cw == 0.0) {
+        // as nvb_pair_score, three chunks of both rows in flight (this runs inside a kernel
+        // compiled for 56 registers)
+        const uint4 *q4 = reinterpret_cast<const uint4 *>(a.gv + qo);
+        const uint4 *f4 = reinterpret_cast<const uint4 *>(a.lv + fo);
+        const int nc = a.Ppad / 16;
+        uint32_t s = 0;
+        for (int c0 = 0; c0 < nc; c0 += 3) {
+            uint4 qq[3], ff[3];
+#pragma unroll
+            for (int u = 0; u < 3; u++)
+                if (c0 + u < nc) { qq[u] = q4[c0 + u]; ff[u] = __ldg(f4 + c0 + u); }
+#pragma unroll
+            for (int u = 0; u < 3; u++)
+                if (c0 + u < nc) {
+                    s = nvb_sad4(qq[u].x, ff[u].x, s); s = nvb_sad4(qq[u].y, ff[u].y, s);
+                    s = nvb_sad4(qq[u].z, ff[u].z, s); s = nvb_sad4(qq[u].w, ff[u].w, s);
+                }
+        }
+        score = s;
+    } else {
+        score = nvb_pair_score(a, qo, fo);
+    }
+    if (score <= thr) {
+        const double d = nvb_exact_diff_rows(a, qo, fo, a.div255);
+        atomicMin(a.exact + g, (unsigned long long)__double_as_longlong(d));
+    }
+}
+
+__device__ __forceinline__ void nvb_tie_help(const StepArgs &a, int n_items)
+{
+    const int T = (int)blockDim.x, chunks = (a.N + T - 1) / T;
+    const long long units = (long long)n_items * chunks;
+    int mine = 0;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        const int item = (int)(u / chunks), ch = (int)(u - (long long)item * chunks);
+        nvb_tie_unit(a, a.tie_items[item].x, a.tie_thr[item], ch * T + (int)threadIdx.x);
+        mine++;
+    }
+    if (mine) {   // CTA-uniform
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(a.tie_count + 1, mine);
+    }
+}
+
+__device__ __forceinline__ void nvb_tie_wait(const StepArgs &a, int b, int n_items)
+{
+    __shared__ int s_tie_ok;
+    const int T = (int)blockDim.x, chunks = (a.N + T - 1) / T;
+    const long long units = (long long)n_items * chunks;
+    if (threadIdx.x == 0) {
+        // patience: ~50 us plus ~5 us per round of units (clock64 ticks at <= 2 GHz)
+        const long long patience = 100000ll + 10000ll * (units / gridDim.x);
+        const long long t0 = clock64();
+        int ok = 1;
+        while (*(volatile int *)(a.tie_count + 1) < units) {
+            if (clock64() - t0 > patience) { ok = 0; break; }
+            __nanosleep(64);
+        }
+        s_tie_ok = ok;
+    }
+    __syncthreads();
+    if (!s_tie_ok) {
+        for (int item = 0; item < n_items; item++) {
+            const int g = a.tie_items[item].x;
+            if (g / a.A != b) continue;   // CTA-uniform
+            const unsigned long long thr = a.tie_thr[item];
+            for (int v0 = 0; v0 < a.N; v0 += T) nvb_tie_unit(a, g, thr, v0 + (int)threadIdx.x);
+        }
+        __threadfence();
+        __syncthreads();
+    }
+    __threadfence();
+}
+
+template <bool NEED_HS, int PH, int PW, bool TIES>
 __global__ void __launch_bounds__(NVB_MS_MAX_THREADS, 7)   // 1024 agents = 7 CTAs per SM: one wave
 k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs sa)
 {
@@ -745,10 +836,16 @@ k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs
     if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 1] = clock64();
     // everything this agent's move needs, requested before the first branch on any of it
     const int stepped = a.ag.stepped[b];
-    const MovePre pre = nvb_move_preload(a, b, nullptr);
+    const int n_items = TIES ? a.tie_count[0] : 0;
+    MovePre pre = nvb_move_preload(a, b, nullptr);
+    if (TIES && n_items > 0) nvb_tie_help(a, n_items);
     if (!stepped) {
         nvb_log_idle(a, b);
         return;
+    }
+    if (TIES && stepped == 2) {
+        nvb_tie_wait(a, b, n_items);
+        if (a.A <= 32 && threadIdx.x < a.A) pre.eb = __ldcg(a.exact + (size_t)b * a.A + threadIdx.x);
     }
     // The window of the NEXT glimpses depends only on the new pose: its TMA loads start as
     // soon as the pose is known and fly during the path scan of update_error; for sweeps of
