@@ -25,6 +25,7 @@ N > 1   = weak scaling: every rank runs its own 1024 agents (independent
           from /root/reference by oracle/build_ref.py) on all host cores.
 """
 import argparse
+import io
 import json
 import os
 import sys
@@ -459,10 +460,29 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="profiling runs: skip the sustained, e2e and cpu legs")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE line, the JSON record: libraries that write to file
+    # descriptor 1 on their own (NCCL's version banner, ...) are sent to stderr for the
+    # duration of the run and the record is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    old_stdout, sys.stdout = sys.stdout, buf
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout = old_stdout
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    lines = [ln for ln in buf.getvalue().splitlines() if ln.strip()]
+    for ln in lines[:-1]:
+        print(ln, file=sys.stderr)
+    if lines:
+        print(lines[-1], flush=True)
 
 
 if __name__ == "__main__":

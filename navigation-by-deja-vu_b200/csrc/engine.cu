@@ -446,7 +446,7 @@ static float sampler_band(const nvb_engine *e)
 }
 
 template <bool HS, int PH, int PW>
-static int launch_sampler_t(nvb_engine *e, const SamplerArgs &sa, int nblocks, size_t smem)
+static int launch_sampler_t(nvb_engine *e, const SamplerArgs &sa, int nblocks, size_t smem, int slices)
 {
     static size_t attr_set[64] = {0};
     size_t &cur = attr_set[e->device & 63];
@@ -454,23 +454,35 @@ static int launch_sampler_t(nvb_engine *e, const SamplerArgs &sa, int nblocks, s
         CK(cudaFuncSetAttribute(k1_sample<HS, PH, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
     }
-    k1_sample<HS, PH, PW><<<nblocks, NVB_SAMPLER_THREADS, smem, e->stream>>>(e->tmap, sa);
+    k1_sample<HS, PH, PW><<<dim3(nblocks, slices), NVB_SAMPLER_THREADS, smem, e->stream>>>(e->tmap, sa);
     e->launches++;
     CK(cudaGetLastError());
     return NVB_OK;
 }
 
-static int launch_sampler(nvb_engine *e, const SamplerArgs &sa, int nblocks)
+// Wide sweeps of few agents (BASELINE configs[2]: 360 headings x 4096 sensor pixels, 1..64
+// agents): one CTA per agent would leave most SMs idle while a handful gather millions of
+// samples, so the headings of an agent are sliced over several CTAs -- which needs the
+// sampler as its own launch (the un-fused step sequence K1, K2, decide, ties, move).
+static int sampler_slices(const nvb_engine *e)
+{
+    if (getenv("NAVSIM_B200_NO_SLICES")) return 1;
+    if ((long long)e->A * e->P < 32768 || e->B >= 2 * e->sm_count) return 1;
+    int s = (2 * e->sm_count + e->B - 1) / e->B;
+    return s < e->A ? s : e->A;
+}
+
+static int launch_sampler(nvb_engine *e, const SamplerArgs &sa, int nblocks, int slices = 1)
 {
     const int nplanes = sa.need_hs ? 3 : 1;
     const size_t smem = e->R > 0 ? nvb_sampler_smem(e->BW, e->BH, nplanes, sa.A)
                                  : nvb_sampler_smem(0, 0, 0, sa.A);
-    if (sa.need_hs) return launch_sampler_t<true, 0, 0>(e, sa, nblocks, smem);
+    if (sa.need_hs) return launch_sampler_t<true, 0, 0>(e, sa, nblocks, smem, slices);
     // sensor-pixel footprints the reference's drivers use get an unrolled sampling loop
-    if (e->ph == 4 && e->pw == 2) return launch_sampler_t<false, 4, 2>(e, sa, nblocks, smem);
-    if (e->ph == 2 && e->pw == 2) return launch_sampler_t<false, 2, 2>(e, sa, nblocks, smem);
-    if (e->ph == 1 && e->pw == 1) return launch_sampler_t<false, 1, 1>(e, sa, nblocks, smem);
-    return launch_sampler_t<false, 0, 0>(e, sa, nblocks, smem);
+    if (e->ph == 4 && e->pw == 2) return launch_sampler_t<false, 4, 2>(e, sa, nblocks, smem, slices);
+    if (e->ph == 2 && e->pw == 2) return launch_sampler_t<false, 2, 2>(e, sa, nblocks, smem, slices);
+    if (e->ph == 1 && e->pw == 1) return launch_sampler_t<false, 1, 1>(e, sa, nblocks, smem, slices);
+    return launch_sampler_t<false, 0, 0>(e, sa, nblocks, smem, slices);
 }
 
 // Cuts the glimpse-tile-major unit list into one contiguous span per CTA.  Every
@@ -1067,7 +1079,7 @@ static SamplerArgs agent_sampler_args(nvb_engine *e)
 static int phase1(nvb_engine *e)
 {
     if (!e->glimpses_pending) {
-        int rc = launch_sampler(e, agent_sampler_args(e), e->B);
+        int rc = launch_sampler(e, agent_sampler_args(e), e->B, sampler_slices(e));
         if (rc) return rc;
     }
     e->glimpses_pending = false;
@@ -1249,7 +1261,7 @@ static int launch_distance_timed(nvb_engine *e, int G)
 static bool fused_step(const nvb_engine *e)
 {
     return e->view_offset == 0 && e->n_total == e->N && e->N <= NVB_FUSED_STEP_MAX_VIEWS &&
-           !getenv("NAVSIM_B200_NO_FUSED_STEP");
+           sampler_slices(e) == 1 && !getenv("NAVSIM_B200_NO_FUSED_STEP");
 }
 
 // One step-batch.  Small un-sharded libraries (fused form): K2, then ONE launch that

@@ -202,7 +202,7 @@ __device__ __forceinline__ SamplerSmem nvb_sampler_layout(const NvbWorld &w, int
 // rotated sensor can reach; the keys of this agent's headings are reset for the next K2.
 template <bool NEED_HS>
 __device__ __forceinline__ bool nvb_sample_window(const CUtensorMap *tmap, const SamplerArgs &a, int b,
-                                                  double x, double y, const SamplerSmem &L)
+                                                  double x, double y, const SamplerSmem &L, int k0, int k1)
 {
     const NvbWorld &w = a.w;
     const int tid = threadIdx.x;
@@ -227,7 +227,7 @@ __device__ __forceinline__ bool nvb_sample_window(const CUtensorMap *tmap, const
         }
     }
     if (a.keys != nullptr)
-        for (int k = tid; k < a.A; k += blockDim.x) a.keys[(size_t)b * a.A + k] = NVB_KEY_NONE;
+        for (int k = k0 + tid; k < k1; k += blockDim.x) a.keys[(size_t)b * a.A + k] = NVB_KEY_NONE;
     return false;
 }
 
@@ -235,11 +235,11 @@ __device__ __forceinline__ bool nvb_sample_window(const CUtensorMap *tmap, const
 // (util.pyx:143-145).  offsets: a.offsets or a copy of them in shared memory.
 __device__ __forceinline__ void nvb_sample_rotations(const SamplerArgs &a, int b, double ang,
                                                      const SamplerSmem &L, const double *offsets,
-                                                     int first_thread, int n_threads)
+                                                     int first_thread, int n_threads, int k0, int k1)
 {
     const int j = (int)threadIdx.x - first_thread;
     if (j < 0 || j >= n_threads) return;
-    for (int k = j; k < a.A; k += n_threads) {
+    for (int k = k0 + j; k < k1; k += n_threads) {
         double c, s;
         if (a.cs != nullptr) {
             c = a.cs[2 * b];
@@ -258,17 +258,18 @@ __device__ __forceinline__ void nvb_sample_rotations(const SamplerArgs &a, int b
 
 template <bool NEED_HS, int PH, int PW>
 __device__ __forceinline__ void nvb_sample_gather(const SamplerArgs &a, int b, double x, double y,
-                                                  const SamplerSmem &L, int32_t *fail_out);
+                                                  const SamplerSmem &L, int32_t *fail_out, int k0, int k1);
 
 // The three steps in one go.  LUT_STAGED: the caller has already copied the quantisation
 // tables to L.lut (they are constant; nvb_sampler_stage_lut).
+// k0, k1: the headings [k0, k1) this CTA samples (all of them, or one slice of a wide sweep).
 template <bool NEED_HS, int PH, int PW, bool LUT_STAGED = false>
 __device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const SamplerArgs &a, int b,
                                                 double x, double y, double ang, uint8_t *smem,
-                                                int32_t *fail_out)
+                                                int32_t *fail_out, int k0, int k1)
 {
     const SamplerSmem L = nvb_sampler_layout<NEED_HS>(a.w, a.A, smem);
-    if (nvb_sample_window<NEED_HS>(tmap, a, b, x, y, L)) {
+    if (nvb_sample_window<NEED_HS>(tmap, a, b, x, y, L, k0, k1)) {
         if (threadIdx.x == 0) *fail_out = -2;
         return;
     }
@@ -277,14 +278,14 @@ __device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const S
         nvb_sampler_stage_lut(a.w, L.lut);
         nvb_sampler_stage_ptab(a.w, L.ptab);
     }
-    nvb_sample_rotations(a, b, ang, L, a.offsets, 0, (int)blockDim.x);
-    nvb_sample_gather<NEED_HS, PH, PW>(a, b, x, y, L, fail_out);
+    nvb_sample_rotations(a, b, ang, L, a.offsets, 0, (int)blockDim.x, k0, k1);
+    nvb_sample_gather<NEED_HS, PH, PW>(a, b, x, y, L, fail_out, k0, k1);
 }
 
 // Step 3 (every thread): wait for the window, gather, block mean, quantise, mask.
 template <bool NEED_HS, int PH, int PW>
 __device__ __forceinline__ void nvb_sample_gather(const SamplerArgs &a, int b, double x, double y,
-                                                  const SamplerSmem &L, int32_t *fail_out)
+                                                  const SamplerSmem &L, int32_t *fail_out, int k0, int k1)
 {
     const NvbWorld &w = a.w;
     const int tid = threadIdx.x;
@@ -329,14 +330,14 @@ __device__ __forceinline__ void nvb_sample_gather(const SamplerArgs &a, int b, d
     // it = k * P + p, p = bi * W + bj: k and p advance incrementally (no divisions in the loop)
     const int T = (int)blockDim.x;
     const int dk = T / w.P, dp = T - dk * w.P;
-    int k = tid / w.P, p = tid - k * w.P;
+    int k = k0 + tid / w.P, p = tid - (tid / w.P) * w.P;
     const bool have_tab = w.P <= NVB_PTAB_MAX;
     const bool linear_out = (w.Ppad == w.P);   // then the output offset of item `it` is just `it`
     // NavBySceneFamiliarity.py:189-190 in units of px0 = bj * pw - Wpx / 2 (exact in FP32)
     const float mask_lo = (float)(w.mask_lo * pw) - half_wf, mask_hi = (float)(w.mask_hi * pw) - half_wf;
     const size_t out0 = (size_t)b * a.A * w.Ppad;
 
-    for (int it = tid; it < a.A * w.P; it += T) {
+    for (int it = k0 * w.P + tid; it < k1 * w.P; it += T) {
         float px0, py0;
         if (have_tab) {
             const float2 e = L.ptab[p];
@@ -459,8 +460,10 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
     } else if (threadIdx.x == 0) {
         a.status[b] = 0;
     }
+    // wide sweeps of few agents: gridDim.y CTAs share an agent, each a slice of its headings
+    const int k0 = (int)((long long)a.A * blockIdx.y / gridDim.y), k1 = (int)((long long)a.A * (blockIdx.y + 1) / gridDim.y);
     nvb_sample_body<NEED_HS, PH, PW>(&tmap, a, b, a.poses[3 * b], a.poses[3 * b + 1], a.poses[3 * b + 2],
-                                     smem_k1, a.status + b);
+                                     smem_k1, a.status + b, k0, k1);
 }
 
 // planar [G][Ppad] x3 -> interleaved [G][P][3] (familiar_scenes / get_sensor_mat layout)

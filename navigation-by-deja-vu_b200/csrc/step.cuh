@@ -566,7 +566,7 @@ k31_step_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArg
     if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 3] = clock64();
     if (!more) return;
     __syncthreads();
-    nvb_sample_body<NEED_HS, PH, PW>(&tmap, sa, b, pose[0], pose[1], pose[2], smem_k31, a.pending_fail + b);
+    nvb_sample_body<NEED_HS, PH, PW>(&tmap, sa, b, pose[0], pose[1], pose[2], smem_k31, a.pending_fail + b, 0, sa.A);
 }
 
 // ---- two launches: [decide + cooperative tie scan] then [move + sample] ------------
@@ -855,12 +855,12 @@ k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs
     const bool short_sweep = a.A <= 32;
     auto window = [&](const double *p) {
         if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 2] = clock64();
-        oob = nvb_sample_window<NEED_HS>(&tmap, sa, b, p[0], p[1], L);
+        oob = nvb_sample_window<NEED_HS>(&tmap, sa, b, p[0], p[1], L, 0, sa.A);
     };
     bool more;
     if (short_sweep) {
         more = nvb_move<0, true>(a, b, nullptr, pre, L.offs, pose, window,
-                                 [&](const double *p) { nvb_sample_rotations(sa, b, p[2], L, L.offs, 32, 32); });
+                                 [&](const double *p) { nvb_sample_rotations(sa, b, p[2], L, L.offs, 32, 32, 0, sa.A); });
     } else {
         more = nvb_move<0, false>(a, b, nullptr, pre, L.offs, pose, window);
     }
@@ -874,8 +874,8 @@ k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs
         if (threadIdx.x == 0) a.pending_fail[b] = -2;
         return;
     }
-    if (!short_sweep) nvb_sample_rotations(sa, b, pose[2], L, L.offs, 0, (int)blockDim.x);
-    nvb_sample_gather<NEED_HS, PH, PW>(sa, b, pose[0], pose[1], L, a.pending_fail + b);
+    if (!short_sweep) nvb_sample_rotations(sa, b, pose[2], L, L.offs, 0, (int)blockDim.x, 0, sa.A);
+    nvb_sample_gather<NEED_HS, PH, PW>(sa, b, pose[0], pose[1], L, a.pending_fail + b, 0, sa.A);
     nvb_tl_stamp(a.tl, 3, 2);
 }
 
