@@ -466,7 +466,8 @@ static int launch_sampler_t(nvb_engine *e, const SamplerArgs &sa, int nblocks, s
 // sampler as its own launch (the un-fused step sequence K1, K2, decide, ties, move).
 static int sampler_slices(const nvb_engine *e)
 {
-    if (getenv("NAVSIM_B200_NO_SLICES")) return 1;
+    static const bool off = getenv("NAVSIM_B200_NO_SLICES") != nullptr;
+    if (off) return 1;
     if ((long long)e->A * e->P < 32768 || e->B >= 2 * e->sm_count) return 1;
     int s = (2 * e->sm_count + e->B - 1) / e->B;
     return s < e->A ? s : e->A;
@@ -1260,8 +1261,9 @@ static int launch_distance_timed(nvb_engine *e, int G)
 
 static bool fused_step(const nvb_engine *e)
 {
+    static const bool off = getenv("NAVSIM_B200_NO_FUSED_STEP") != nullptr;
     return e->view_offset == 0 && e->n_total == e->N && e->N <= NVB_FUSED_STEP_MAX_VIEWS &&
-           sampler_slices(e) == 1 && !getenv("NAVSIM_B200_NO_FUSED_STEP");
+           sampler_slices(e) == 1 && !off;
 }
 
 // One step-batch.  Small un-sharded libraries (fused form): K2, then ONE launch that
