@@ -41,6 +41,9 @@ struct DistArgs {
 };
 
 #define NVB_DIST_THREADS 256
+#ifndef NVB_K2_UNROLL_MAX
+#define NVB_K2_UNROLL_MAX 5   /* rows of up to this many 16-byte chunks get a fully unrolled SAD loop */
+#endif
 
 __device__ __forceinline__ void nvb_cp_async16(void *dst, const void *src, int src_bytes)
 {
@@ -237,7 +240,8 @@ k2_sad_v(DistArgs a)
         }
 
         const uint8_t *st = smem + (it % STAGES) * C::STAGE_BYTES;
-#pragma unroll(CPR <= 5 ? CPR : 1)
+        constexpr int UNR = (CPR <= NVB_K2_UNROLL_MAX) ? CPR : 1;
+#pragma unroll(UNR)
         for (int c = 0; c < CPR; c++) {
             uint4 av[MG];
 #pragma unroll
