@@ -274,3 +274,53 @@ def test_dropin_class_matches_oracle(mods, name):
     # get_sensor_mat keeps the reference's exceptions
     with pytest.raises(navsim.OutOfLandscapeBoundsException):
         nsf.get_sensor_mat((1.0, 1.0), 0.0)
+
+
+@pytest.mark.parametrize("buffers", ["pinned", "pageable", "fresh"])
+@pytest.mark.parametrize("name", ["c1_small", "ties"])
+def test_host_driven_step_io_matches_oracle(mods, name, buffers):
+    """nvb_agents_step_io: the host hands in the poses of every step and reads the results back
+    (bench.py's end-to-end form), with pinned buffers, pageable buffers and buffers that
+    change on every call.  All must walk the oracle's trajectories."""
+    import torch
+    navsim, util, O = mods
+    L, w, tpath, pose, frames = build_case(name)
+    K = 14
+    eng = navsim.NavEngine(L, **w)
+    ow = O.World(L, **w)
+    assert eng.train_from_path(tpath) == (0, -1)
+    assert ow.train_from_path(tpath) == (0, -1)
+    poses = np.vstack([np.asarray(pose)[None], agent_grid(tpath, w)])[:12]
+    B = len(poses)
+    eng.set_agents(poses, K + 5)
+
+    def alloc():
+        if buffers == "pinned":
+            t = (torch.empty((B, 3), dtype=torch.float64).pin_memory(), torch.empty((B, 3), dtype=torch.float64).pin_memory(),
+                 torch.empty((B,), dtype=torch.int16).pin_memory(), torch.empty((B,), dtype=torch.float64).pin_memory())
+            return t, [x.numpy() for x in t]
+        a = [np.empty((B, 3)), np.empty((B, 3)), np.empty(B, np.int16), np.empty(B)]
+        return a, a
+    keep, (h_in, h_pose, h_best, h_fam) = alloc()
+    h_in[:] = poses
+    best, pos, fam = [], [], []
+    for i in range(K):
+        if buffers == "fresh":   # new arrays on every call: the pointers never repeat
+            cur = h_in.copy()
+            keep, (h_in, h_pose, h_best, h_fam) = alloc()
+            h_in[:] = cur
+        eng.step_io(h_in, 1, h_best, h_pose, h_fam)
+        best.append(h_best.copy()); pos.append(h_pose.copy()); fam.append(h_fam.copy())
+        h_in[:] = h_pose
+    best, pos, fam = np.array(best), np.array(pos), np.array(fam)
+    for b, p in enumerate(poses):
+        ag = ow.new_agent(*p)
+        r = ow.run(ag, K, log_afam=True)
+        n = r["completed"] + (1 if r["status"] in (1, -1) else 0)
+        assert n > 0
+        assert np.array_equal(best[:n, b], r["best_idx"][:n]), (name, buffers, b)
+        assert np.all(best[n:, b] == -1)
+        assert np.allclose(pos[:n, b], r["pos"][:n], rtol=0, atol=POS_TOL)
+        assert np.allclose(fam[:n, b], r["afam"][:n].max(axis=1), rtol=FAM_RTOL, atol=0)
+    st = eng.state()
+    assert eng.steps_done == K
