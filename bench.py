@@ -239,21 +239,23 @@ def run_ours(args):
     h_pose = torch.empty((B, 3), dtype=torch.float64).pin_memory()
     h_best = torch.empty((B,), dtype=torch.int16).pin_memory()
     h_fam = torch.empty((B,), dtype=torch.float64).pin_memory()
-    h_in.numpy()[:] = poses
+    a_in, a_pose, a_best, a_fam = h_in.numpy(), h_pose.numpy(), h_best.numpy(), h_fam.numpy()
+    step_io = eng.bind_step_io(a_in, a_best, a_pose, a_fam)   # same pinned buffers every call
+    a_in[:] = poses
     eng.set_agents(poses)
     for _ in range(W):
-        eng.step_io(h_in.numpy(), 1, h_best.numpy(), h_pose.numpy(), h_fam.numpy())
-        h_in.copy_(h_pose)
+        step_io()
+        a_in[:] = a_pose
     eng.set_agents(poses)
-    h_in.numpy()[:] = poses
+    a_in[:] = poses
     barrier()
     t0 = time.perf_counter()
     for i in range(1 if args.quick else K):
         if i and i % rewind_every == 0:
             eng.rewind()
-            h_in.numpy()[:] = poses
-        eng.step_io(h_in.numpy(), 1, h_best.numpy(), h_pose.numpy(), h_fam.numpy())
-        h_in.copy_(h_pose)            # the caller feeds the new poses back in, like a host-driven loop
+            a_in[:] = poses
+        step_io()                     # H2D poses, one step-batch, D2H results, one synchronisation
+        a_in[:] = a_pose              # the caller feeds the new poses back in, like a host-driven loop
     torch.cuda.synchronize()
     t_e2e = max_over_ranks(time.perf_counter() - t0) * (K if args.quick else 1)
     e2e_result_checksum = float(np.nansum(h_fam.numpy()))

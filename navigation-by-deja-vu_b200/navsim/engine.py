@@ -253,6 +253,19 @@ class NavEngine(object):
         check(self._lib.nvb_agents_step_io(self._h, ptr(poses_in), int(nsteps), ptr(best_idx),
                                            ptr(poses_out), ptr(step_fam)))
 
+    def bind_step_io(self, poses_in, best_idx, poses_out, step_fam, nsteps=1):
+        """step_io for a host-driven loop that reuses its buffers: resolves the four array
+        pointers once and returns a zero-argument callable doing one call each time."""
+        fn, h = self._lib.nvb_agents_step_io, self._h
+        args = (ptr(poses_in), int(nsteps), ptr(best_idx), ptr(poses_out), ptr(step_fam))
+        keep = (poses_in, best_idx, poses_out, step_fam)
+
+        def call(_keep=keep):
+            rc = fn(h, *args)
+            if rc:
+                check(rc)
+        return call
+
     def set_options(self, use_graph=True, kernel_timing=False):
         check(self._lib.nvb_set_options(self._h, int(bool(use_graph)), int(bool(kernel_timing))))
 
