@@ -152,7 +152,10 @@ int nvb_agents_rewind(nvb_engine *e);
  * nsteps step-batches, the last step's results back on the host, one
  * synchronisation: the per-call form a host-driven loop uses (the reference's
  * step_forward() contract, NavBySceneFamiliarity.py:279, for B agents).
- * best_idx [B], poses_out [B][3], step_fam [B]; any may be NULL. */
+ * best_idx [B], poses_out [B][3], step_fam [B]; any may be NULL.
+ * When the same page-locked buffers are passed call after call (nsteps == 1) the
+ * engine binds them into the kernels of the step: the poses are read from, and the
+ * results written to, the host buffers directly, with no copy operations. */
 int nvb_agents_step_io(nvb_engine *e, const double *poses_in, int nsteps, int16_t *best_idx,
                        double *poses_out, double *step_fam);
 /* Current state (synchronises).  Any pointer may be NULL.  poses [B][3],

@@ -29,6 +29,12 @@ struct SamplerArgs {
     unsigned long long *keys;  // [B*A] reset to "none" (agent mode) or nullptr
     float band;              // FP32 fast path: distance from a rounding tie below which FP64 decides
     long long *dbg;          // optional [B][8] clock64 checkpoints (tuning aid), else nullptr
+    // host-driven form without copy operations: the poses are read straight from the caller's
+    // page-locked buffer (device-mapped), written through to `poses_dst`, and the parked
+    // failure of the agent is cleared; all nullptr otherwise
+    const double *poses_src;
+    double *poses_dst;
+    int32_t *pending_clear;
 };
 
 #define NVB_SAMPLER_THREADS 256
@@ -455,6 +461,25 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
     nvb_grid_dep_wait();
     extern __shared__ __align__(128) uint8_t smem_k1[];
     const int b = blockIdx.x;
+    double px, py, pa;
+    if (a.poses_src != nullptr) {
+        // zero-copy input: one thread fetches the pose over the host link, everybody uses it;
+        // the first slice also refreshes the device copy (stopped agents included, like the
+        // host-to-device copy this replaces)
+        __shared__ double s_pose_in[3];
+        if (threadIdx.x == 0) {
+            for (int q = 0; q < 3; q++) {
+                const double v = a.poses_src[3 * b + q];
+                s_pose_in[q] = v;
+                if (blockIdx.y == 0) a.poses_dst[3 * b + q] = v;
+            }
+            if (blockIdx.y == 0 && a.pending_clear != nullptr) a.pending_clear[b] = 0;
+        }
+        __syncthreads();
+        px = s_pose_in[0]; py = s_pose_in[1]; pa = s_pose_in[2];
+    } else {
+        px = a.poses[3 * b]; py = a.poses[3 * b + 1]; pa = a.poses[3 * b + 2];
+    }
     if (a.agent_mode) {
         if (!(a.status[b] == 0 && a.completed[b] < a.budget[b])) return;
     } else if (threadIdx.x == 0) {
@@ -462,8 +487,7 @@ k1_sample(const __grid_constant__ CUtensorMap tmap, SamplerArgs a)
     }
     // wide sweeps of few agents: gridDim.y CTAs share an agent, each a slice of its headings
     const int k0 = (int)((long long)a.A * blockIdx.y / gridDim.y), k1 = (int)((long long)a.A * (blockIdx.y + 1) / gridDim.y);
-    nvb_sample_body<NEED_HS, PH, PW>(&tmap, a, b, a.poses[3 * b], a.poses[3 * b + 1], a.poses[3 * b + 2],
-                                     smem_k1, a.status + b, k0, k1);
+    nvb_sample_body<NEED_HS, PH, PW>(&tmap, a, b, px, py, pa, smem_k1, a.status + b, k0, k1);
 }
 
 // planar [G][Ppad] x3 -> interleaved [G][P][3] (familiar_scenes / get_sensor_mat layout)

@@ -70,6 +70,11 @@ struct StepArgs {
     unsigned long long *dmin2;   // [B] squared distance to the path (FP64 bits), long-path form
     int pdl_early;               // trigger the dependent launch at the top of every kernel
     long long *tl;               // tuning aid: timeline stamps (nvb_tl_stamp) or nullptr
+    // host-driven form without copy operations: results of the step written straight into the
+    // caller's page-locked buffers (device-mapped); each nullptr when not wanted
+    int16_t *out_best;           // [B]
+    double *out_poses;           // [B][3]
+    double *out_sfam;            // [B]
     double cover_thr2;           // largest double whose sqrt is <= coverage_factor * step_size (host)
 };
 
@@ -385,6 +390,9 @@ __device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigne
             a.ag.poses[3 * b] = x;
             a.ag.poses[3 * b + 1] = y;
             a.ag.poses[3 * b + 2] = ang;
+            if (a.out_best != nullptr) a.out_best[b] = (int16_t)best;
+            if (a.out_sfam != nullptr) a.out_sfam[b] = best_fam;
+            if (a.out_poses != nullptr) { a.out_poses[3 * b] = x; a.out_poses[3 * b + 1] = y; a.out_poses[3 * b + 2] = ang; }
             if (logging) {
                 a.log_best[(size_t)t * a.B + b] = (int16_t)best;
                 a.log_pose[((size_t)t * a.B + b) * 3] = x;
@@ -489,8 +497,14 @@ __device__ __forceinline__ void nvb_log_idle(const StepArgs &a, int b)
 {
     const int tid = threadIdx.x;
     const int t = *a.step_counter;
-    if (!(t >= 0 && t < a.log_cap)) return;
     const double nan = __longlong_as_double(0x7FF8000000000000ll);
+    if (tid == 0) {
+        if (a.out_best != nullptr) a.out_best[b] = -1;
+        if (a.out_sfam != nullptr) a.out_sfam[b] = nan;
+        if (a.out_poses != nullptr)
+            for (int q = 0; q < 3; q++) a.out_poses[3 * b + q] = a.ag.poses[3 * b + q];
+    }
+    if (!(t >= 0 && t < a.log_cap)) return;
     if (tid == 0) {
         a.log_best[(size_t)t * a.B + b] = -1;
         for (int q = 0; q < 3; q++) a.log_pose[((size_t)t * a.B + b) * 3 + q] = a.ag.poses[3 * b + q];
