@@ -115,6 +115,7 @@ struct nvb_engine {
     // into the host buffers (zero-copy); keyed on the four pointers
     cudaGraphExec_t graph_zc = nullptr;
     const void *zc_key[4] = {nullptr, nullptr, nullptr, nullptr}, *seen_key[4] = {nullptr, nullptr, nullptr, nullptr};
+    void *zc_dev[4] = {nullptr, nullptr, nullptr, nullptr};   // device-mapped views the graph was captured with
     const double *zc_in = nullptr;     // device-mapped views of the caller's buffers, set while capturing
     int16_t *zc_best = nullptr;
     double *zc_pose = nullptr, *zc_fam = nullptr;
@@ -1425,6 +1426,15 @@ static void *mapped_view(const void *host)
     return dev;
 }
 
+// The buffers behind the same addresses may have been freed and re-allocated as pageable memory
+// since the graph was captured: the mapping is verified on every call (a sub-microsecond query).
+static bool still_mapped(const void *const key[4], void *const dev[4])
+{
+    for (int i = 0; i < 4; i++)
+        if (key[i] && mapped_view(key[i]) != dev[i]) return false;
+    return true;
+}
+
 // Captures the per-call step-batch with the caller's buffers bound into the kernels (see graph_zc).
 // Failure is not fatal: the copy-based form keeps working.
 static int capture_zero_copy_graph(nvb_engine *e, const void *const key[4])
@@ -1457,6 +1467,7 @@ static int capture_zero_copy_graph(nvb_engine *e, const void *const key[4])
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) { e->graph_zc = nullptr; cudaGetLastError(); return NVB_OK; }
     memcpy(e->zc_key, key, sizeof e->zc_key);
+    memcpy(e->zc_dev, v, sizeof e->zc_dev);
     return NVB_OK;
 }
 
@@ -1472,7 +1483,7 @@ extern "C" int nvb_agents_step_io(nvb_engine *e, const double *poses_in, int nst
     const bool per_call = poses_in != nullptr && nsteps == 1 && e->use_graph && !e->timing;
     if (per_call && e->graph_zc && !e->graph_dirty && e->graph_io_log_ptr == e->log_best &&
         e->graph_io_log_cap == e->log_cap && e->steps_done + 1 <= e->log_cap &&
-        memcmp(key, e->zc_key, sizeof key) == 0) {
+        memcmp(key, e->zc_key, sizeof key) == 0 && still_mapped(key, e->zc_dev)) {
         // one graph launch, no copy operations: K1 reads the poses from the caller's buffer,
         // the move writes the results into the caller's buffers
         CK(cudaGraphLaunch(e->graph_zc, e->stream));
