@@ -75,6 +75,7 @@ struct nvb_engine {
     int N = 0;
     uint8_t *d_lh = nullptr, *d_ls = nullptr, *d_lv = nullptr;
     double *d_path = nullptr;
+    double *d_pblk = nullptr;       // [ceil(n_path / 16)][4]: bounding circle (cx, cy, r, -) of 16 consecutive path points
     int n_path = 0;
     long long view_offset = 0, n_total = 0;
     // glimpse buffers
@@ -332,7 +333,7 @@ extern "C" void nvb_engine_destroy(nvb_engine *e)
                     e->d_tie_items, e->d_tie_thr, e->d_tie_next, e->d_tie_ready, e->ag.poses, e->ag.status, e->ag.completed,
                     e->ag.budget, e->ag.nav_frames, e->ag.err_sum, e->ag.err_n, e->ag.coverage,
                     e->ag.stepped, e->d_step, e->log_best, e->log_pose, e->log_sfam, e->log_afam,
-                    e->d_poses0, e->d_budget0, e->d_spans, e->d_pending, e->d_dmin2};
+                    e->d_poses0, e->d_budget0, e->d_spans, e->d_pending, e->d_dmin2, e->d_pblk};
     for (int i = 0; i < NVB_P2P_MAX_RANKS; i++)
         if (e->p2p_opened[i]) cudaIpcCloseMemHandle(e->p2p_opened[i]);
     free_dev(e->d_xarea); free_dev(e->d_p2p_seq); free_dev(e->d_p2p_err);
@@ -776,6 +777,25 @@ static int set_path(nvb_engine *e, const double *path, int n)
     if (rc) return rc;
     CK(cudaMemcpy(e->d_path, path, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
     e->n_path = n;
+    // Bounding circles of blocks of NVB_PATH_BLOCK consecutive points: update_error first
+    // discards whole blocks that cannot hold the nearest point or a covered point (step.cuh).
+    // The radius is inflated so that it bounds the true distances whatever the rounding.
+    const int nb = (n + NVB_PATH_BLOCK - 1) / NVB_PATH_BLOCK;
+    std::vector<double> blk((size_t)4 * nb);
+    for (int j = 0; j < nb; j++) {
+        const int n0 = j * NVB_PATH_BLOCK, n1 = n0 + NVB_PATH_BLOCK < n ? n0 + NVB_PATH_BLOCK : n;
+        double cx = 0, cy = 0;
+        for (int i = n0; i < n1; i++) { cx += path[2 * i]; cy += path[2 * i + 1]; }
+        cx /= (n1 - n0); cy /= (n1 - n0);
+        double r = 0;
+        for (int i = n0; i < n1; i++) {
+            const double d = hypot(path[2 * i] - cx, path[2 * i + 1] - cy);
+            if (d > r) r = d;
+        }
+        blk[4 * j] = cx; blk[4 * j + 1] = cy; blk[4 * j + 2] = r * (1.0 + 1e-12) + 1e-9; blk[4 * j + 3] = 0.0;
+    }
+    if ((rc = alloc_dev(&e->d_pblk, (size_t)4 * nb))) return rc;
+    CK(cudaMemcpy(e->d_pblk, blk.data(), sizeof(double) * 4 * nb, cudaMemcpyHostToDevice));
     return NVB_OK;
 }
 
@@ -1038,6 +1058,7 @@ static StepArgs make_step_args(nvb_engine *e, int fake, int log_afam)
     s.gv = e->d_gv; s.gh = e->d_gh; s.gs = e->d_gs;
     s.lv = e->d_lv; s.lh = e->d_lh; s.ls = e->d_ls;
     s.path = e->d_path; s.n_path = e->n_path;
+    s.pblk = getenv("NAVSIM_B200_NO_PATH_BLOCKS") ? nullptr : e->d_pblk;
     s.view_offset = e->view_offset;
     s.keys = e->d_keys; s.exact = e->d_exact;
     s.idx_bits = (e->cw == 0.0) ? 32 : 28;

@@ -70,6 +70,7 @@ struct StepArgs {
     unsigned long long *dmin2;   // [B] squared distance to the path (FP64 bits), long-path form
     int pdl_early;               // trigger the dependent launch at the top of every kernel
     long long *tl;               // tuning aid: timeline stamps (nvb_tl_stamp) or nullptr
+    const double *pblk;          // [ceil(n_path / NVB_PATH_BLOCK)][4] bounding circles of path blocks, or nullptr
     // host-driven form without copy operations: results of the step written straight into the
     // caller's page-locked buffers (device-mapped); each nullptr when not wanted
     int16_t *out_best;           // [B]
@@ -78,6 +79,8 @@ struct StepArgs {
     double cover_thr2;           // largest double whose sqrt is <= coverage_factor * step_size (host)
 };
 
+#define NVB_PATH_BLOCK 16      /* path points per bounding circle (update_error prefilter) */
+#define NVB_PATH_LIVE_MAX 1024  /* blocks the prefilter can list: paths up to NVB_PATH_SPLIT points */
 #define NVB_STEP_THREADS 128   /* == NVB_SAMPLER_THREADS: k31_step_sample runs both bodies */
 #define NVB_STEP_MAX_A_SMEM 512 /* headings whose exact differences are kept in shared memory */
 #define NVB_TIE_Q_CHUNKS 64     /* fused tie scan: glimpse rows up to 1 KB are staged in shared memory */
@@ -436,6 +439,68 @@ __device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigne
     double m = __longlong_as_double(0x7FF0000000000000ll);
     if (MODE == 2) {
         m = __longlong_as_double((long long)a.dmin2[b]);
+    } else if (a.pblk != nullptr && one_pass && a.n_path <= NVB_PATH_LIVE_MAX * NVB_PATH_BLOCK) {
+        // Prefilter: a block of 16 consecutive path points lies inside a circle (c, r).  Its
+        // points are no nearer than |p - c| - r and one of them is no farther than |p - c| + r.
+        // With U = the smallest such upper bound, the nearest point and every point within
+        // thr (coverage) sit in blocks whose lower bound is <= max(U, thr); only those blocks
+        // are scanned, with exactly the arithmetic of the full scan, so the minimum and the
+        // coverage marks are the same.  (The scanning warps meet at a named barrier: warp 1
+        // may be busy with the rotations.)
+        __shared__ double s_ub[8];
+        __shared__ unsigned short s_live[NVB_PATH_LIVE_MAX];
+        __shared__ int s_nlive;
+        const int n_blk = (a.n_path + NVB_PATH_BLOCK - 1) / NVB_PATH_BLOCK;
+        const bool scanning = !warp1;
+        const int sid = (!W1_HOOK || tid < 32) ? tid : tid - 32;   // index among the scanning threads
+        if (scanning) {
+            if (sid == 0) s_nlive = 0;
+            double ub = __longlong_as_double(0x7FF0000000000000ll);
+            for (int j = sid; j < n_blk; j += scan_n) {
+                const double2 cc = __ldg(reinterpret_cast<const double2 *>(a.pblk) + 2 * j);
+                const double2 cr = __ldg(reinterpret_cast<const double2 *>(a.pblk) + 2 * j + 1);
+                const double3 c = make_double3(cc.x, cc.y, cr.x);
+                const double ex = __dsub_rn(c.x, x), ey = __dsub_rn(c.y, y);
+                const double dc = __dsqrt_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
+                ub = fmin(ub, __dadd_rn(dc, c.z));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ub = fmin(ub, __shfl_xor_sync(0xFFFFFFFFu, ub, o));
+            if ((tid & 31) == 0) s_ub[tid >> 5] = ub;
+            asm volatile("bar.sync 1, %0;" ::"r"(scan_n) : "memory");
+            // U = max(thr, min over the scanning warps of their upper bounds)
+            double umin = __longlong_as_double(0x7FF0000000000000ll);
+            for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++)
+                if (!(W1_HOOK && wq == 1)) umin = fmin(umin, s_ub[wq]);
+            const double U = fmax(thr, umin);
+            for (int j = sid; j < n_blk; j += scan_n) {
+                const double2 cc = __ldg(reinterpret_cast<const double2 *>(a.pblk) + 2 * j);
+                const double2 cr = __ldg(reinterpret_cast<const double2 *>(a.pblk) + 2 * j + 1);
+                const double3 c = make_double3(cc.x, cc.y, cr.x);
+                const double ex = __dsub_rn(c.x, x), ey = __dsub_rn(c.y, y);
+                const double dc = __dsqrt_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
+                // slack far above the rounding of dc and of the comparison
+                if (__dsub_rn(dc, c.z) <= __dadd_rn(U, 1e-9 * (1.0 + dc))) s_live[atomicAdd(&s_nlive, 1)] = (unsigned short)j;
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(scan_n) : "memory");
+            const int n_live = s_nlive;
+            for (int idx = sid; idx < n_live * NVB_PATH_BLOCK; idx += scan_n) {
+                const int n = (int)s_live[idx / NVB_PATH_BLOCK] * NVB_PATH_BLOCK + (idx % NVB_PATH_BLOCK);
+                if (n < a.n_path) {
+                    const double2 pt = __ldg(path + n);
+                    const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
+                    const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    m = fmin(m, d2);
+                    if (d2 <= thr2) a.ag.coverage[(size_t)b * a.n_path + n] = 1;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        if ((tid & 31) == 0) s_red[tid >> 5] = m;
+        __syncthreads();
+        m = s_red[0];
+        for (int wq = 1; wq < (int)(blockDim.x >> 5); wq++) m = fmin(m, s_red[wq]);
     } else {
 #pragma unroll 4
         for (int n = scan_id; n < a.n_path; n += scan_n) {
@@ -839,9 +904,14 @@ k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs
     nvb_sampler_stage_lut(sa.w, L.lut);
     nvb_sampler_stage_ptab(sa.w, L.ptab);
     for (int k = threadIdx.x; k < a.A; k += blockDim.x) L.offs[k] = a.offsets[k];
-    if (a.n_path <= 4096)
+    if (a.pblk != nullptr) {   // update_error reads the block bounds of the whole path, then a few blocks
+        const int bytes = ((a.n_path + NVB_PATH_BLOCK - 1) / NVB_PATH_BLOCK) * 32;
+        for (int o = threadIdx.x * 128; o < bytes; o += blockDim.x * 128)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(a.pblk) + o));
+    } else if (a.n_path <= 4096) {
         for (int o = threadIdx.x * 128; o < a.n_path * 16; o += blockDim.x * 128)
             asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(a.path) + o));
+    }
     if (sa.dbg && threadIdx.x == 0) sa.dbg[blockIdx.x * 8 + 0] = clock64();
     __syncthreads();
     nvb_grid_dep_wait();

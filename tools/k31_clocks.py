@@ -25,7 +25,10 @@ if os.environ.get("NAVSIM_B200_STEP_FORM") != "1":
     f = out2[1][ok]
     base = d[:, 2]   # pose published
     for i, n in enumerate(["window requested", "warp 1 hook done", "warp 0 scanned", "warp 2 scanned", "reduced", "bookkeeping done"]):
-        x = (f[:, i] - base) / 1.965e3
+        got = f[:, i] > 0
+        if not got.any():
+            continue   # stamp not on the path taken (e.g. the full scan when the block prefilter runs)
+        x = (f[got, i] - base[got]) / 1.965e3
         print("   pose -> %-20s mean %6.2f us  p10 %6.2f  p90 %6.2f" % (n, x.mean(), np.percentile(x, 10), np.percentile(x, 90)))
 tot = (d[:, 6] - d[:, 0]) / 1.965e3
 print("total per CTA  mean %.2f us  max %.2f us   (n=%d)" % (tot.mean(), tot.max(), len(d)))
