@@ -58,6 +58,10 @@ const char *nvb_last_error(void);
 const char *nvb_version(void);
 /* Blocks until everything launched on the engine's stream has finished. */
 int nvb_sync(nvb_engine *e);
+/* The cudaStream_t the engine launches on (its own, or the one given at creation): a caller
+ * that touches the engine's device buffers from another stream (the NCCL MIN all-reduce of
+ * the view-sharded mode, navsim/sharded.py) orders the two streams with events on it. */
+void *nvb_stream_handle(nvb_engine *e);
 
 /* ---- world: landscape, sensor, heading sweep, navigation parameters ----- */
 /* Landscape: uint8 HSV, shape (rows, cols, 3), arbitrary byte strides

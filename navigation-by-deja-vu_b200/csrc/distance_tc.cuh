@@ -1,0 +1,341 @@
+// distance_tc.cuh -- K2 on the 5th-generation tensor cores (tcgen05, sm_100a): the
+// glimpse-vs-library sum of absolute differences as an EXACT int8 contraction.
+//
+// Replaces the same reference lines as distance.cuh (sads_hsv_metric,
+// navsim/util.pyx:28-73, with chem_weight == 0, plus the per-heading max of
+// navsim/NavBySceneFamiliarity.py:313) for sensors quantised to few levels
+// (n_sensor_levels, NavBySceneFamiliarity.py:100-104,175-186: default 5).
+//
+// After quantisation a V pixel takes one of n levels l_0 < l_1 < ... < l_{n-1}
+// (the distinct values of the quantisation table).  With the thermometer code
+// T_k(v) = [v > l_k], k = 0..n-2, and weights w_k = l_{k+1} - l_k,
+//     |a - b| = sum_k w_k [T_k(a) != T_k(b)] = sum_k w_k (1 - s_k(a) s_k(b)) / 2,
+// s_k = 2 T_k - 1 in {-1, +1}.  Summed over the P sensor pixels:
+//     SAD(a, b) = (C - dot(A, B)) / 2,   C = P * sum_k w_k = P * (l_{n-1} - l_0),
+// A[k, p] = w_k s_k(a_p) (int8, |w_k| <= 127: larger weights are split into several
+// planes), B[k, p] = s_k(b_p) (int8, +-1).  dot is an int8 x int8 -> int32 GEMM of
+// shape [G x K] . [K x N], K = planes * P, exact in 32-bit integers: the smallest SAD is
+// the largest dot, and the integer SAD this kernel reports is bit-identical to the
+// byte-SIMD kernel's (k2_sad_v).
+//
+// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0      TMA producer: 128 x KCH-byte glimpse chunk + NT x KCH-byte view chunk per
+//               pipeline stage (cp.async.bulk.tensor.2d, 64- or 128-byte swizzle)
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::i8, M = 128, N = NT, K = 32 per
+//               instruction, accumulator in TMEM (2 buffers of 256 columns)
+//   warps 2..5  epilogue: tcgen05.ld of the finished accumulator (one glimpse row per
+//               thread), key = -256 * dot + column folded with a 3-input minimum, one
+//               64-bit atomicMin per glimpse row and work item
+// Work items (glimpse tile x view tile) are cut into one contiguous span per CTA exactly
+// like k2_sad_v's units.
+#pragma once
+#include "common.cuh"
+
+#define NVB_TC_THREADS 192
+#define NVB_TC_TM 128          /* glimpse rows per tile (UMMA M) */
+#define NVB_TC_MAX_PLANES 8
+
+struct TcPlanes {
+    int n_planes;                          // thermometer planes (after splitting heavy weights)
+    int8_t weight[NVB_TC_MAX_PLANES];      // w_k, 1..127
+    uint8_t thr_level[NVB_TC_MAX_PLANES];  // plane k is set where level index > thr_level[k]
+};
+
+struct TcArgs {
+    int G, N;                    // glimpses, views (local shard)
+    int n_vt;                    // view tiles
+    int kchunks;                 // K-chunks of KCH bytes per row
+    const int *spans;            // [gridDim.x + 1] item boundaries per CTA
+    unsigned long long *keys;    // [G], pre-set to NVB_KEY_NONE
+    long long view_offset;       // global index of local view 0
+    int sad_const;               // C = P * sum of plane weights
+    int *step_counter;           // resident loop: bumped once per launch, else nullptr
+    int *tie_count;
+    int pdl_early;
+    long long *tl;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------
+__device__ __forceinline__ void nvb_tma_load_2d(void *dst, const CUtensorMap *tmap, int x, int y, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(nvb_smem_u32(dst)),
+        "l"(tmap), "r"(x), "r"(y), "r"(nvb_smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void nvb_prefetch_tmap(const CUtensorMap *tmap)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void nvb_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void nvb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void nvb_tmem_alloc(uint32_t *slot, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(nvb_smem_u32(slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void nvb_tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem], int8 x int8 -> int32, issued by ONE thread
+__device__ __forceinline__ void nvb_umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the MMAs issued so far by this thread arrive on `bar` when they have completed
+__device__ __forceinline__ void nvb_umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(nvb_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void nvb_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 32 consecutive columns (one accumulator row slice per thread)
+__device__ __forceinline__ void nvb_tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void nvb_tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// Shared-memory matrix descriptor of a K-major operand tile whose rows are KCH bytes
+// (KCH = 64: 64-byte swizzle, KCH = 128: 128-byte swizzle), rows packed, groups of 8 rows
+// 8 * KCH bytes apart.  Bits: [0,14) start address >> 4, [16,30) leading byte offset >> 4
+// (unused for swizzled K-major, 1), [32,46) stride byte offset >> 4, [46,48) version = 1
+// (sm_100), [61,64) layout: 2 = 128-byte swizzle, 4 = 64-byte swizzle.
+template <int KCH>
+__device__ __forceinline__ uint64_t nvb_umma_desc(const void *tile)
+{
+    const uint32_t addr = nvb_smem_u32(tile);
+    uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * KCH) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(KCH == 128 ? 2 : 4) << 61;
+    return d;
+}
+
+// Instruction descriptor, kind::i8: bits [4,6) accumulator format 2 = S32, [7,10) A format
+// 1 = signed 8 bit, [10,13) B format 1 = signed 8 bit, bit 15 / 16 A / B major 0 = K,
+// [17,23) N >> 3, [24,29) M >> 4.
+__host__ __device__ constexpr uint32_t nvb_umma_idesc_i8(int M, int N)
+{
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Folds W (32 or 16) accumulator columns [c0, c0 + W) of this thread's row into the running
+// minimum of -256 * dot + column (largest dot first, then lowest column); columns >= nvalid
+// (past the end of the library) are skipped.
+template <int W>
+__device__ __forceinline__ int nvb_tc_fold(uint32_t taddr, int c0, int nvalid, int best)
+{
+    uint32_t r[W];
+    if (W == 32) nvb_tmem_ld32(taddr + (uint32_t)c0, reinterpret_cast<uint32_t (&)[32]>(r));
+    else nvb_tmem_ld16(taddr + (uint32_t)c0, reinterpret_cast<uint32_t (&)[16]>(r));
+    nvb_tmem_wait_ld();
+    if (c0 + W <= nvalid) {
+#pragma unroll
+        for (int j = 0; j + 1 < W; j += 2)
+            best = __vimin3_s32(best, (int)r[j] * -256 + (c0 + j), (int)r[j + 1] * -256 + (c0 + j + 1));
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; j++)
+            if (c0 + j < nvalid) best = min(best, (int)r[j] * -256 + (c0 + j));
+    }
+    return best;
+}
+
+template <int KCH, int NT, int STAGES>
+struct TcCfg {
+    static constexpr int TM = NVB_TC_TM;
+    static constexpr int A_BYTES = TM * KCH;
+    static constexpr int B_BYTES = NT * KCH;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM = STAGE_BYTES * STAGES + 1024 /* alignment slack */ + 256 /* barriers */;
+    static_assert(KCH == 64 || KCH == 128, "K chunk is one 64- or 128-byte swizzle atom");
+    static_assert(NT % 16 == 0 && NT >= 16 && NT <= 256, "UMMA N for M = 128");
+    static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles start on swizzle-pattern boundaries");
+};
+
+template <int KCH, int NT, int STAGES>
+__global__ void __launch_bounds__(NVB_TC_THREADS, 1)
+k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, TcArgs a)
+{
+    using C = TcCfg<KCH, NT, STAGES>;
+    extern __shared__ uint8_t smem_tc_raw[];
+    // 1024-byte alignment in the shared window (the swizzle pattern is a function of the address)
+    uint8_t *smem = smem_tc_raw + ((1024u - (nvb_smem_u32(smem_tc_raw) & 1023u)) & 1023u);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGE_BYTES * STAGES);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tfull = empty + STAGES;    // accumulator buffer ready for the epilogue
+    uint64_t *tempty = tfull + 2;        // accumulator buffer drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    nvb_tl_stamp(a.tl, 0, 0);
+    if (a.pdl_early) nvb_grid_dep_launch();
+    if (warp == 0 && lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) {
+            nvb_mbar_init(full + s, 1);
+            nvb_mbar_init(empty + s, 1);
+        }
+        nvb_mbar_init(tfull + 0, 1); nvb_mbar_init(tfull + 1, 1);
+        nvb_mbar_init(tempty + 0, 4); nvb_mbar_init(tempty + 1, 4);
+        nvb_fence_barrier_init();
+        nvb_prefetch_tmap(&tm_a);
+        nvb_prefetch_tmap(&tm_b);
+    }
+    if (warp == 2) nvb_tmem_alloc(tmem_slot, 512);
+    nvb_tc_fence_before();
+    __syncthreads();
+    nvb_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int u0 = a.spans[blockIdx.x], u1 = a.spans[blockIdx.x + 1];
+
+    nvb_grid_dep_wait();   // the glimpses are written by the previous kernel of the step sequence
+    nvb_tl_stamp(a.tl, 0, 1);
+    if (a.step_counter != nullptr && blockIdx.x == 0 && tid == 0) {
+        *a.step_counter += 1;
+        a.tie_count[0] = 0;
+        a.tie_count[1] = 0;
+    }
+
+    if (warp == 0) {
+        // ---- TMA producer
+        int s = 0;
+        uint32_t ph = 0;
+        int gt = u0 / a.n_vt, vt = u0 - gt * a.n_vt;
+        for (int u = u0; u < u1; u++) {
+            for (int kc = 0; kc < a.kchunks; kc++) {
+                if (lane == 0) {
+                    nvb_mbar_wait(empty + s, ph ^ 1u);
+                    uint8_t *st = smem + s * C::STAGE_BYTES;
+                    nvb_mbar_expect_tx(full + s, (uint32_t)C::STAGE_BYTES);
+                    nvb_tma_load_2d(st, &tm_a, kc * KCH, gt * C::TM, full + s);
+                    nvb_tma_load_2d(st + C::A_BYTES, &tm_b, kc * KCH, vt * NT, full + s);
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+            if (++vt == a.n_vt) { vt = 0; gt++; }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer
+        constexpr uint32_t idesc = nvb_umma_idesc_i8(C::TM, NT);
+        int s = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        for (int u = u0; u < u1; u++, it++) {
+            const int buf = it & 1;
+            const uint32_t tph = (uint32_t)(it >> 1) & 1u;
+            if (lane == 0) {
+                nvb_mbar_wait(tempty + buf, tph ^ 1u);   // the epilogue has drained this buffer
+                nvb_tc_fence_after();
+            }
+            __syncwarp();
+            for (int kc = 0; kc < a.kchunks; kc++) {
+                if (lane == 0) {
+                    nvb_mbar_wait(full + s, ph);
+                    nvb_tc_fence_after();
+                    const uint8_t *st = smem + s * C::STAGE_BYTES;
+                    const uint64_t da = nvb_umma_desc<KCH>(st), db = nvb_umma_desc<KCH>(st + C::A_BYTES);
+#pragma unroll
+                    for (int j = 0; j < KCH / 32; j++)   // 32 bytes of K per instruction: +2 in 16-byte units
+                        nvb_umma_i8(tmem_base + (uint32_t)(buf * 256), da + (uint64_t)(2 * j), db + (uint64_t)(2 * j),
+                                    idesc, (uint32_t)((kc | j) != 0));
+                    nvb_umma_commit(empty + s);                       // stage free once these MMAs have read it
+                    if (kc == a.kchunks - 1) nvb_umma_commit(tfull + buf);   // accumulator complete
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else {
+        // ---- epilogue: warp w may touch TMEM lanes 32 * (w % 4) .. + 31
+        const int ew = warp & 3;
+        const int row = ew * 32 + lane;
+        int gt = u0 / a.n_vt, vt = u0 - gt * a.n_vt;
+        int it = 0;
+        for (int u = u0; u < u1; u++, it++) {
+            const int buf = it & 1;
+            const uint32_t tph = (uint32_t)(it >> 1) & 1u;
+            nvb_mbar_wait(tfull + buf, tph);
+            nvb_tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256);
+            const int nvalid = min(NT, a.N - vt * NT);
+            int best = 0x7FFFFFFF;   // min over columns of -256 * dot + column
+#pragma unroll
+            for (int c0 = 0; c0 < NT; c0 += 32) {
+                if (NT - c0 >= 32) best = nvb_tc_fold<32>(taddr, c0, nvalid, best);
+                else best = nvb_tc_fold<16>(taddr, c0, nvalid, best);
+            }
+            nvb_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) nvb_mbar_arrive(tempty + buf);
+            const int g = gt * C::TM + row;
+            if (g < a.G && best != 0x7FFFFFFF) {
+                const int col = best & 255;
+                const int dot = -(best >> 8);
+                const unsigned long long sad = (unsigned long long)((a.sad_const - dot) >> 1);
+                const unsigned long long v = (unsigned long long)(a.view_offset + (long long)vt * NT + col);
+                atomicMin(a.keys + g, (sad << 32) | v);
+            }
+            if (++vt == a.n_vt) { vt = 0; gt++; }
+        }
+    }
+    nvb_tc_fence_before();
+    __syncthreads();
+    if (warp == 2) nvb_tmem_dealloc(tmem_base, 512);
+    nvb_tl_stamp(a.tl, 0, 2);
+}
+
+// ---- operand encoding ---------------------------------------------------------------
+// src [rows][Ppad] uint8 (quantised V plane) -> dst [rows][Kpad] int8, k = plane * P + p;
+// glimpse side (IS_A): +-w_k, library side: +-1.  Bytes k >= planes * P stay zero (the
+// buffer is zeroed once when it is allocated).  level_of[v] = index of v among the levels.
+template <bool IS_A>
+__global__ void k_tc_encode(const uint8_t *src, long long rows, int P, int Ppad, int Kpad, TcPlanes pl,
+                            const uint8_t *level_of, int8_t *dst)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * P) return;
+    const long long r = i / P;
+    const int p = (int)(i - r * P);
+    const int lvl = level_of[src[(size_t)r * Ppad + p]];
+    int8_t *o = dst + (size_t)r * Kpad + p;
+#pragma unroll
+    for (int k = 0; k < NVB_TC_MAX_PLANES; k++)
+        if (k < pl.n_planes) {
+            const int sgn = (lvl > (int)pl.thr_level[k]) ? 1 : -1;
+            o[(size_t)k * P] = (int8_t)(IS_A ? sgn * (int)pl.weight[k] : sgn);
+        }
+}

@@ -260,6 +260,7 @@ static int ensure_glimpse_cap(nvb_engine *e, long long G)
 {
     if (G <= e->Gcap) return NVB_OK;
     e->graph_dirty = true;
+    e->glimpses_pending = false;   // the buffers that held the pre-sampled glimpses are replaced
     int rc;
     const size_t bytes = (size_t)G * e->Ppad;
     if ((rc = alloc_dev(&e->d_gh, bytes))) return rc;
@@ -354,6 +355,8 @@ extern "C" int nvb_sync(nvb_engine *e)
 }
 
 extern "C" int64_t nvb_launch_count(nvb_engine *e) { return e->launches; }
+
+extern "C" void *nvb_stream_handle(nvb_engine *e) { return (void *)e->stream; }
 
 extern "C" int nvb_set_landscape(nvb_engine *e, const uint8_t *hsv, int rows, int cols,
                                  ptrdiff_t s_row, ptrdiff_t s_col, ptrdiff_t s_chan)
@@ -735,6 +738,9 @@ extern "C" int nvb_glimpse_batch(nvb_engine *e, const double *poses, const doubl
     CK(cudaSetDevice(e->device));
     int rc = ensure_glimpse_cap(e, G);
     if (rc) return rc;
+    // the resident glimpse buffers are reused as scratch: glimpses sampled ahead for the next
+    // step of the stepping loop are overwritten, so that step samples again (phase1 / run_steps)
+    e->glimpses_pending = false;
     int32_t *d_status = nullptr;
     uint8_t *d_out = nullptr;
     CK(cudaMalloc(&d_status, sizeof(int32_t) * G));
@@ -901,6 +907,7 @@ static int upload_queries(nvb_engine *e, const uint8_t *scenes_q, int G)
 {
     int rc = ensure_glimpse_cap(e, G);
     if (rc) return rc;
+    e->glimpses_pending = false;   // as nvb_glimpse_batch: the pre-sampled glimpses (and keys) are overwritten
     uint8_t *d_in = nullptr;
     const long long n = (long long)G * e->P;
     CK(cudaMalloc(&d_in, (size_t)n * 3));
@@ -1001,6 +1008,12 @@ extern "C" int nvb_agents_set(nvb_engine *e, const double *poses, const int32_t 
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
     int rc;
+    if (e->p2p_on && (long long)B * e->A > e->p2p.cap) {
+        // the exchange area exported to the peers is too small for this batch: the peers hold
+        // mappings of the old area, so the exchange is switched off until a new export + attach
+        e->p2p_on = false;
+        e->graph_dirty = true;
+    }
     if (B != e->B) {
         e->graph_dirty = true;
         if ((rc = alloc_dev(&e->ag.poses, (size_t)3 * B))) return rc;
@@ -1228,6 +1241,9 @@ static int launch_k31(nvb_engine *e, const StepArgs &s)
 static int p2p_exchange(nvb_engine *e, unsigned long long *values)
 {
     if (!e->p2p_on) return NVB_OK;
+    if ((long long)e->B * e->A > e->p2p.cap)
+        return fail(NVB_E_INVALID, "exchange area holds %lld values but the batch has %lld: export and attach again",
+                    e->p2p.cap, (long long)e->B * e->A);
     CK(launch_seq(k_p2p_min, dim3(1), dim3(NVB_P2P_THREADS), 0, e->stream, e->p2p, values, e->B * e->A));
     e->launches++;
     return NVB_OK;
@@ -1741,6 +1757,10 @@ extern "C" int nvb_p2p_export(nvb_engine *e, void *handle64)
     CK(cudaStreamSynchronize(e->stream));
     const long long cap = (long long)e->B * e->A;
     const size_t bytes = sizeof(P2PArea) + sizeof(unsigned long long) * (size_t)(2 * cap);
+    e->p2p_on = false;
+    e->graph_dirty = true;
+    for (int i = 0; i < NVB_P2P_MAX_RANKS; i++)
+        if (e->p2p_opened[i]) { cudaIpcCloseMemHandle(e->p2p_opened[i]); e->p2p_opened[i] = nullptr; }
     free_dev(e->d_xarea);
     e->d_xarea = nullptr;
     CK(cudaMalloc((void **)&e->d_xarea, bytes));

@@ -26,6 +26,7 @@ SIGNATURES = {
     "nvb_last_error": (C.c_char_p, []),
     "nvb_version": (C.c_char_p, []),
     "nvb_sync": (_i, [_vp]),
+    "nvb_stream_handle": (_vp, [_vp]),
     "nvb_set_landscape": (_i, [_vp, _vp, _i, _i, _sz, _sz, _sz]),
     "nvb_set_sensor": (_i, [_vp, _i, _i, _i, _i, _vp, _i]),
     "nvb_set_saccade": (_i, [_vp, _i, _vp]),

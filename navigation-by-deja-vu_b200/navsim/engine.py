@@ -282,6 +282,11 @@ class NavEngine(object):
         check(self._lib.nvb_sync(self._h))
 
     @property
+    def stream_handle(self):
+        """cudaStream_t of the engine's stream as an integer."""
+        return int(self._lib.nvb_stream_handle(self._h) or 0)
+
+    @property
     def steps_done(self):
         return self._lib.nvb_agents_steps_done(self._h)
 

@@ -79,14 +79,39 @@ class ShardedStepper(object):
         if keys is None:
             keys, exact = engine_reduction_tensors(engine)
         self.keys, self.exact = keys, exact
+        # phase() only ENQUEUES kernels on the engine's stream (by default a non-blocking stream
+        # of its own) while the all-reduce runs on torch's current stream: the two are ordered
+        # explicitly around every reduction.  Engines without a CUDA stream (the CPU stand-in
+        # of the gloo tests) need nothing.
+        self._engine_stream = None
+        if keys.is_cuda:
+            import torch
+            handle = getattr(engine, "stream_handle", None)
+            if handle is None:
+                raise ValueError("a CUDA engine must expose stream_handle for the reduction ordering")
+            self._torch = torch
+            self._engine_stream = torch.cuda.ExternalStream(handle, device=keys.device)
+
+    def _all_reduce_min(self, buf):
+        dist = self.dist
+        es = self._engine_stream
+        if es is None:
+            dist.all_reduce(buf, op=dist.ReduceOp.MIN, group=self.group)
+            return
+        cur = self._torch.cuda.current_stream(buf.device)
+        same = cur.cuda_stream == es.cuda_stream
+        if not same:
+            cur.wait_stream(es)          # the kernels that wrote `buf` are done before NCCL reads it
+        dist.all_reduce(buf, op=dist.ReduceOp.MIN, group=self.group)
+        if not same:
+            es.wait_stream(cur)          # the reduced values have landed before the next phase reads them
 
     def step(self, nsteps=1, fake=False, log_afam=False):
-        dist = self.dist
         for _ in range(int(nsteps)):
             self.engine.phase(1, fake=fake, log_afam=log_afam)
-            dist.all_reduce(self.keys, op=dist.ReduceOp.MIN, group=self.group)
+            self._all_reduce_min(self.keys)
             self.engine.phase(2, fake=fake, log_afam=log_afam)
-            dist.all_reduce(self.exact, op=dist.ReduceOp.MIN, group=self.group)
+            self._all_reduce_min(self.exact)
             self.engine.phase(3, fake=fake, log_afam=log_afam)
 
 

@@ -15,6 +15,7 @@ the hot path and therefore plain host NumPy ("out of scope"):
 """
 import ctypes as C
 import math
+import zlib
 
 import numpy as np
 
@@ -23,6 +24,7 @@ from ._cabi import check, ptr
 
 _default_engine = None
 _landscape_key = None
+_landscape_ref = None     # strong reference: the cached array's address cannot be handed to another array
 
 
 def _engine():
@@ -118,19 +120,25 @@ def fill_sensor_from(sensor, xpos, ypos, angle, landscape):
     """util.pyx:137-168: fills `sensor` (Hpx, Wpx, 3) in place with
     nearest-neighbour samples of `landscape` rotated about (xpos, ypos).
     Raises IndexError where the reference's bounds-checked indexing does."""
-    global _landscape_key
+    global _landscape_key, _landscape_ref
     sensor = _as_u8("sensor", sensor, 3)
     landscape = _as_u8("landscape", landscape, 3)
     if not sensor.flags.writeable:
         raise ValueError("buffer source array is read-only")
     lib = _cabi.lib()
     h = _engine()
-    key = (landscape.ctypes.data, landscape.shape, landscape.strides)
+    # The device copy of the landscape is reused while the caller keeps passing the same
+    # array: same address / shape / strides, the array object kept alive here (the reference's
+    # driver makes a fresh landscape.copy() per trial, scripts/run_experiment.py:186-193, and
+    # a freed copy's address is readily reused), and the same checksum of a 64 x 64 sample
+    # grid.  In-place edits between the sampled pixels still need invalidate_landscape_cache().
+    key = (landscape.ctypes.data, landscape.shape, landscape.strides, _sample_checksum(landscape))
     if key != _landscape_key:
         s = landscape.strides
         check(lib.nvb_set_landscape(h, ptr(landscape), landscape.shape[0], landscape.shape[1],
                                     s[0], s[1], s[2]))
         _landscape_key = key
+        _landscape_ref = landscape
     rot = -(0.5 * math.pi - float(angle))       # util.pyx:143
     out = sensor if sensor.flags.c_contiguous else np.empty(sensor.shape, np.uint8)
     rc = check(lib.nvb_fill_sensor(h, ptr(out), sensor.shape[0], sensor.shape[1], float(xpos),
@@ -141,11 +149,17 @@ def fill_sensor_from(sensor, xpos, ypos, angle, landscape):
         sensor[...] = out
 
 
+def _sample_checksum(a):
+    r, c = max(1, a.shape[0] // 64), max(1, a.shape[1] // 64)
+    return zlib.crc32(a[::r, ::c].tobytes())
+
+
 def invalidate_landscape_cache():
     """Forget the device copy made by fill_sensor_from (call after mutating the
     landscape array in place)."""
-    global _landscape_key
+    global _landscape_key, _landscape_ref
     _landscape_key = None
+    _landscape_ref = None
 
 
 # ---- off the hot path: host NumPy -------------------------------------------

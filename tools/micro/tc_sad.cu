@@ -1,0 +1,296 @@
+// tc_sad.cu -- SURVEY.md H6 measured: the exact thermometer / int8 tensor-core form of the
+// glimpse-vs-library SAD (csrc/distance_tc.cuh, tcgen05 kind::i8) against the byte-SIMD
+// kernel (csrc/distance.cuh, k2_sad_v) on the same inputs, same box, CUDA events.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o tools/micro/tc_sad tools/micro/tc_sad.cu -lcuda
+//   tools/micro/tc_sad [G N P levels reps]          (defaults: C2 = 10240 1414 80 5 20)
+//
+// Prints one line per variant: exact (vs a CPU scan of a row subsample) and us per launch.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "../../navigation-by-deja-vu_b200/csrc/distance.cuh"
+#include "../../navigation-by-deja-vu_b200/csrc/distance_tc.cuh"
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            fprintf(stderr, "%s failed: %s (%s:%d)\n", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            exit(2);                                                                               \
+        }                                                                                          \
+    } while (0)
+
+typedef CUresult (*PFN_encode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encode g_encode;
+
+static CUtensorMap make_map(void *base, long long rows, int Kpad, int kch, int box_rows)
+{
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)Kpad};
+    cuuint32_t box[2] = {(cuuint32_t)kch, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          kch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "cuTensorMapEncodeTiled failed: %d\n", (int)r); exit(2); }
+    return m;
+}
+
+static std::vector<int> make_spans(long long units, int n_cta)
+{
+    std::vector<int> s(n_cta + 1);
+    const long long base = units / n_cta, rem = units % n_cta;
+    long long u = 0;
+    for (int c = 0; c < n_cta; c++) { s[c] = (int)u; u += base + (c < rem ? 1 : 0); }
+    s[n_cta] = (int)units;
+    return s;
+}
+
+__global__ void k_fill(unsigned long long *p, long long n, unsigned long long v)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+struct Ctx {
+    int G, N, P, Ppad, sms;
+    uint8_t *d_g, *d_l;
+    unsigned long long *d_keys;
+    std::vector<unsigned long long> ref;   // CPU keys of the checked rows
+    std::vector<int> rows;
+    int reps;
+};
+
+static bool check(Ctx &c, const char *name)
+{
+    std::vector<unsigned long long> keys(c.G);
+    CK(cudaMemcpy(keys.data(), c.d_keys, sizeof(unsigned long long) * c.G, cudaMemcpyDeviceToHost));
+    long long bad = 0;
+    for (size_t i = 0; i < c.rows.size(); i++)
+        if (keys[c.rows[i]] != c.ref[i]) {
+            if (bad < 5)
+                fprintf(stderr, "  %s: row %d got (%llu, %llu) want (%llu, %llu)\n", name, c.rows[i],
+                        keys[c.rows[i]] >> 32, keys[c.rows[i]] & 0xFFFFFFFFull, c.ref[i] >> 32, c.ref[i] & 0xFFFFFFFFull);
+            bad++;
+        }
+    return bad == 0;
+}
+
+template <int KCH, int NT, int STAGES>
+static void run_tc(Ctx &c, const TcPlanes &pl, const uint8_t *d_level_of, const char *name)
+{
+    using C = TcCfg<KCH, NT, STAGES>;
+    const int Kreal = pl.n_planes * c.P, Kpad = (Kreal + KCH - 1) / KCH * KCH;
+    int8_t *d_a, *d_b;
+    CK(cudaMalloc(&d_a, (size_t)c.G * Kpad));
+    CK(cudaMalloc(&d_b, (size_t)c.N * Kpad));
+    CK(cudaMemset(d_a, 0, (size_t)c.G * Kpad));
+    CK(cudaMemset(d_b, 0, (size_t)c.N * Kpad));
+    auto kern = k2_tc<KCH, NT, STAGES>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    const CUtensorMap ma = make_map(d_a, c.G, Kpad, KCH, C::TM), mb = make_map(d_b, c.N, Kpad, KCH, NT);
+    const int n_gt = (c.G + C::TM - 1) / C::TM, n_vt = (c.N + NT - 1) / NT;
+    const long long items = (long long)n_gt * n_vt;
+    const int n_cta = (int)std::min<long long>(c.sms, items);
+    std::vector<int> spans = make_spans(items, n_cta);
+    int *d_spans;
+    CK(cudaMalloc(&d_spans, sizeof(int) * spans.size()));
+    CK(cudaMemcpy(d_spans, spans.data(), sizeof(int) * spans.size(), cudaMemcpyHostToDevice));
+    TcArgs a{};
+    a.G = c.G; a.N = c.N; a.n_vt = n_vt; a.kchunks = Kpad / KCH; a.spans = d_spans; a.keys = c.d_keys;
+    a.view_offset = 0; a.sad_const = 0;
+    for (int k = 0; k < pl.n_planes; k++) a.sad_const += c.P * (int)pl.weight[k];
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float enc_ms = 0, best = 1e9f, total = 0;
+    for (int r = 0; r < c.reps + 2; r++) {
+        k_fill<<<(c.G + 255) / 256, 256>>>(c.d_keys, c.G, NVB_KEY_NONE);
+        CK(cudaEventRecord(e0));
+        k_tc_encode<true><<<(unsigned)(((long long)c.G * c.P + 255) / 256), 256>>>(c.d_g, c.G, c.P, c.Ppad, Kpad, pl, d_level_of, d_a);
+        CK(cudaEventRecord(e1));
+        if (r == 0) k_tc_encode<false><<<(unsigned)(((long long)c.N * c.P + 255) / 256), 256>>>(c.d_l, c.N, c.P, c.Ppad, Kpad, pl, d_level_of, d_b);
+        CK(cudaDeviceSynchronize());
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (r >= 2) enc_ms += ms;
+        CK(cudaEventRecord(e0));
+        kern<<<n_cta, NVB_TC_THREADS, C::SMEM>>>(ma, mb, a);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        CK(cudaGetLastError());
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (r >= 2) { total += ms; best = std::min(best, ms); }
+    }
+    const bool ok = check(c, name);
+    // back-to-back launches (launch latency amortised): keys are not reset, atomicMin is idempotent
+    CK(cudaEventRecord(e0));
+    for (int r = 0; r < c.reps; r++) kern<<<n_cta, NVB_TC_THREADS, C::SMEM>>>(ma, mb, a);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float b2b;
+    CK(cudaEventElapsedTime(&b2b, e0, e1));
+    const double ops = 2.0 * c.G * (double)c.N * Kreal;
+    printf("{\"kernel\": \"%s\", \"exact\": %s, \"us_mean\": %.2f, \"us_min\": %.2f, \"us_back_to_back\": %.2f, "
+           "\"encode_glimpses_us\": %.2f, \"items\": %lld, \"ctas\": %d, \"K\": %d, \"Kpad\": %d, \"tensor_TOPs\": %.1f}\n",
+           name, ok ? "true" : "false", total / c.reps * 1e3, best * 1e3, b2b / c.reps * 1e3, enc_ms / c.reps * 1e3,
+           items, n_cta, Kreal, Kpad, ops / (b2b / c.reps * 1e-3) / 1e12);
+    fflush(stdout);
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_spans);
+}
+
+template <int TY, int MG, int MV, int CPR, int STAGES, bool BULK>
+static void run_simd(Ctx &c, const char *name)
+{
+    using C = DistCfg<TY, MG, MV, CPR, STAGES>;
+    auto kern = k2_sad_v<TY, MG, MV, CPR, STAGES, BULK>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NVB_DIST_THREADS, C::SMEM));
+    const int n_gt = (c.G + C::TG - 1) / C::TG, n_vt = (c.N + C::TN - 1) / C::TN;
+    const long long units = (long long)n_gt * n_vt;
+    const int n_cta = (int)std::min<long long>((long long)c.sms * occ, units);
+    std::vector<int> spans = make_spans(units, n_cta);
+    int *d_spans;
+    CK(cudaMalloc(&d_spans, sizeof(int) * spans.size()));
+    CK(cudaMemcpy(d_spans, spans.data(), sizeof(int) * spans.size(), cudaMemcpyHostToDevice));
+    DistArgs a{};
+    a.gv = c.d_g; a.lv = c.d_l; a.G = c.G; a.N = c.N; a.Ppad = c.Ppad; a.nk = 1; a.n_vt = n_vt; a.spans = d_spans;
+    a.keys = c.d_keys; a.idx_bits = 32;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e9f, total = 0;
+    for (int r = 0; r < c.reps + 2; r++) {
+        k_fill<<<(c.G + 255) / 256, 256>>>(c.d_keys, c.G, NVB_KEY_NONE);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        kern<<<n_cta, NVB_DIST_THREADS, C::SMEM>>>(a);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        CK(cudaGetLastError());
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (r >= 2) { total += ms; best = std::min(best, ms); }
+    }
+    const bool ok = check(c, name);
+    CK(cudaEventRecord(e0));
+    for (int r = 0; r < c.reps; r++) kern<<<n_cta, NVB_DIST_THREADS, C::SMEM>>>(a);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float b2b;
+    CK(cudaEventElapsedTime(&b2b, e0, e1));
+    printf("{\"kernel\": \"%s\", \"exact\": %s, \"us_mean\": %.2f, \"us_min\": %.2f, \"us_back_to_back\": %.2f, "
+           "\"units\": %lld, \"ctas\": %d, \"int_TOPs\": %.1f}\n",
+           name, ok ? "true" : "false", total / c.reps * 1e3, best * 1e3, b2b / c.reps * 1e3, units, n_cta,
+           2.0 * c.G * (double)c.N * c.P / (b2b / c.reps * 1e-3) / 1e12);
+    fflush(stdout);
+    cudaFree(d_spans);
+}
+
+int main(int argc, char **argv)
+{
+    Ctx c;
+    c.G = argc > 1 ? atoi(argv[1]) : 10240;
+    c.N = argc > 2 ? atoi(argv[2]) : 1414;
+    c.P = argc > 3 ? atoi(argv[3]) : 80;
+    const int nlev = argc > 4 ? atoi(argv[4]) : 5;
+    c.reps = argc > 5 ? atoi(argv[5]) : 20;
+    c.Ppad = (c.P + 15) / 16 * 16;
+    if (c.P != 80) { fprintf(stderr, "this probe instantiates the byte-SIMD kernel for P = 80 only\n"); }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    c.sms = prop.multiProcessorCount;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    g_encode = (PFN_encode)fn;
+
+    // quantisation levels as NavBySceneFamiliarity.py:178-186 produces them (float32 ops)
+    std::vector<int> levels;
+    {
+        int last = -1;
+        for (int x = 0; x < 256; x++) {
+            float b = (float)x / 255.0f * (float)(nlev - 1);
+            b = nearbyintf(b);
+            b = b / (float)(nlev - 1) * 255.0f;
+            const int v = (int)(uint8_t)b;
+            if (v != last) { levels.push_back(v); last = v; }
+        }
+    }
+    TcPlanes pl{};
+    std::vector<uint8_t> level_of(256, 0);
+    for (size_t i = 0; i < levels.size(); i++) level_of[levels[i]] = (uint8_t)i;
+    for (size_t k = 0; k + 1 < levels.size(); k++) {
+        int w = levels[k + 1] - levels[k];
+        const int parts = (w + 126) / 127;
+        for (int q = 0; q < parts; q++) {
+            const int wq = w / (parts - q);
+            pl.weight[pl.n_planes] = (int8_t)wq;
+            pl.thr_level[pl.n_planes] = (uint8_t)k;
+            pl.n_planes++;
+            w -= wq;
+        }
+    }
+    fprintf(stderr, "levels %zu, planes %d, G %d N %d P %d\n", levels.size(), pl.n_planes, c.G, c.N, c.P);
+
+    // smooth-ish random views; every glimpse is a perturbed copy of some view so that small
+    // minima and exact ties occur (argmin = lowest index among equal sums)
+    std::mt19937 rng(1234);
+    std::vector<uint8_t> lib((size_t)c.N * c.Ppad, 0), gl((size_t)c.G * c.Ppad, 0);
+    for (int n = 0; n < c.N; n++) {
+        int lv = rng() % nlev;
+        for (int p = 0; p < c.P; p++) {
+            if (rng() % 3 == 0) lv = std::min(nlev - 1, std::max(0, lv + (int)(rng() % 3) - 1));
+            lib[(size_t)n * c.Ppad + p] = (uint8_t)levels[lv];
+        }
+    }
+    for (int n = 1; n < c.N; n += 97) memcpy(&lib[(size_t)n * c.Ppad], &lib[(size_t)(n - 1) * c.Ppad], c.Ppad);   // duplicate views
+    for (int g = 0; g < c.G; g++) {
+        const int src = rng() % c.N;
+        for (int p = 0; p < c.P; p++) {
+            uint8_t v = lib[(size_t)src * c.Ppad + p];
+            if (rng() % 5 == 0) v = (uint8_t)levels[rng() % nlev];
+            gl[(size_t)g * c.Ppad + p] = v;
+        }
+    }
+    for (int g = 0; g < c.G; g += 8) c.rows.push_back(g);
+    c.rows.push_back(c.G - 1);
+    for (int g : c.rows) {
+        unsigned long long best = ~0ull;
+        for (int n = 0; n < c.N; n++) {
+            unsigned s = 0;
+            for (int p = 0; p < c.P; p++) s += (unsigned)abs((int)gl[(size_t)g * c.Ppad + p] - (int)lib[(size_t)n * c.Ppad + p]);
+            const unsigned long long key = ((unsigned long long)s << 32) | (unsigned)n;
+            if (key < best) best = key;
+        }
+        c.ref.push_back(best);
+    }
+
+    CK(cudaMalloc(&c.d_g, gl.size()));
+    CK(cudaMalloc(&c.d_l, lib.size()));
+    CK(cudaMalloc(&c.d_keys, sizeof(unsigned long long) * c.G));
+    CK(cudaMemcpy(c.d_g, gl.data(), gl.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.d_l, lib.data(), lib.size(), cudaMemcpyHostToDevice));
+    uint8_t *d_level_of;
+    CK(cudaMalloc(&d_level_of, 256));
+    CK(cudaMemcpy(d_level_of, level_of.data(), 256, cudaMemcpyHostToDevice));
+
+    const char *only = getenv("TC_ONLY");
+    if (c.P == 80 && !only) {
+        run_simd<16, 3, 15, 5, 3, true>(c, "k2_sad_v 48x240 (byte SIMD)");
+        run_simd<16, 4, 16, 5, 3, true>(c, "k2_sad_v 64x256 (byte SIMD)");
+    }
+    run_tc<64, 256, 8>(c, pl, d_level_of, "k2_tc kch64 nt256 s8 (tcgen05 i8)");
+    run_tc<64, 240, 8>(c, pl, d_level_of, "k2_tc kch64 nt240 s8 (tcgen05 i8)");
+    run_tc<128, 256, 4>(c, pl, d_level_of, "k2_tc kch128 nt256 s4 (tcgen05 i8)");
+    run_tc<64, 128, 8>(c, pl, d_level_of, "k2_tc kch64 nt128 s8 (tcgen05 i8)");
+    return 0;
+}
