@@ -230,9 +230,19 @@ def run_ours(args):
     # placed inside the graph without breaking the programmatic launch overlap they measure)
     eng.rewind()
     tl = eng.timeline(8)
-    k2_graph_ms = (tl["k2_sad_v"][2] - tl["k2_sad_v"][0]) * 1e-3 if "k2_sad_v" in tl else None
+    k2_graph_ms = (tl["k2"][2] - tl["k2"][0]) * 1e-3 if "k2" in tl else None
     eng.rewind()
+    k2_name = eng.distance_kernel
     sad_peak = eng.probe_sad_peak(8192)           # pixel-compares / s, register resident
+    mma_peak = eng.probe_mma_peak(4096) if k2_name == "k2_tc" else None   # int8 ops / s, operands resident in smem
+    # the byte-SIMD kernel on the same batch (it stays the path for chem_weight > 0 and for
+    # sensors with more than 9 levels): timed alone, reported beside the tensor-core kernel
+    simd_alone_ms = None
+    if k2_name == "k2_tc":
+        eng.set_distance_kernel(simd_only=True)
+        simd_alone_ms = eng.time_distance_kernel(20)
+        eng.set_distance_kernel(simd_only=False)
+        eng.rewind()
 
     # ---- e2e: per step pinned host poses in, results out, one sync
     h_in = torch.empty((B, 3), dtype=torch.float64).pin_memory()
@@ -272,25 +282,54 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     k2_s = (k2_ms / max(k2_n, 1)) * 1e-3
-    ops = 2.0 * B * A * N * P                    # algorithmic integer ops per launch
     alg_bytes = N * P + B * A * P + 8 * B * A    # library + glimpses + keys, V plane only (chem_weight 0)
-    roofline = {
-        "kernel": "k2_sad_v (distance, fused min/argmin)",
-        "bound": "int_alu",
-        "achieved": ops / k2_s / 1e12, "peak": 2.0 * sad_peak / 1e12, "unit": "TOP/s",
-        "frac": (ops / k2_s) / (2.0 * sad_peak),
-        "peak_source": "VABSDIFF4.U8.ACC issue-rate probe measured in this run (nvb_probe_sad_peak); "
-                       "not in MEASURED_PEAKS.json",
-        "launch_ms": k2_s * 1e3, "launch_ms_alone": k2_alone_ms, "launches_timed": k2_n,
-        "launch_ms_in_graph": k2_graph_ms,
-        "frac_in_graph": (ops / (k2_graph_ms * 1e-3)) / (2.0 * sad_peak) if k2_graph_ms else None,
+    if k2_name == "k2_tc":
+        # tensor-core form, ops = 2 * G * N * K with K = thermometer planes x sensor pixels
+        k_dim = eng.tc_planes * P
+        ops = 2.0 * B * A * N * k_dim
+        bf16 = peaks.get("bf16_tflops", 1590.0)
+        roofline = {
+            "kernel": "k2_tc (distance on tcgen05 int8: exact thermometer contraction, fused min/argmin)",
+            "bound": "tensor",
+            "achieved": ops / k2_s / 1e12, "peak": 2.0 * bf16, "unit": "TOP/s",
+            "frac": (ops / k2_s / 1e12) / (2.0 * bf16),
+            "peak_source": "2 x bf16_tflops of %s (kind::i8 issues K = 32 per instruction where bf16 issues 16, same "
+                           "cycles); the int8 issue rate measured in this run with operands resident in shared "
+                           "memory is in peak_int8_probe" % ("MEASURED_PEAKS.json" if "bf16_tflops" in peaks else "fallback"),
+            "peak_int8_probe": mma_peak / 1e12 if mma_peak and mma_peak > 0 else None,
+            "frac_of_int8_probe": (ops / k2_s) / mma_peak if mma_peak and mma_peak > 0 else None,
+            "ops_per_launch": ops, "k_planes_x_pixels": k_dim,
+            "launch_ms": k2_s * 1e3, "launch_ms_alone": k2_alone_ms, "launches_timed": k2_n,
+            "launch_ms_in_graph": k2_graph_ms,
+            "frac_in_graph": (ops / (k2_graph_ms * 1e-3) / 1e12) / (2.0 * bf16) if k2_graph_ms else None,
+            "byte_simd_kernel": {
+                "kernel": "k2_sad_v", "launch_ms_alone": simd_alone_ms,
+                "int_alu_TOPs": 2.0 * B * A * N * P / (simd_alone_ms * 1e-3) / 1e12 if simd_alone_ms else None,
+                "int_alu_peak_TOPs": 2.0 * sad_peak / 1e12,
+                "frac": (2.0 * B * A * N * P / (simd_alone_ms * 1e-3)) / (2.0 * sad_peak) if simd_alone_ms else None,
+                "note": "same batch, same exact minima; the path for chem_weight > 0 and sensors of more than 9 levels"},
+        }
+    else:
+        ops = 2.0 * B * A * N * P                    # algorithmic integer ops per launch
+        roofline = {
+            "kernel": "k2_sad_v (distance, fused min/argmin)",
+            "bound": "int_alu",
+            "achieved": ops / k2_s / 1e12, "peak": 2.0 * sad_peak / 1e12, "unit": "TOP/s",
+            "frac": (ops / k2_s) / (2.0 * sad_peak),
+            "peak_source": "VABSDIFF4.U8.ACC issue-rate probe measured in this run (nvb_probe_sad_peak); "
+                           "not in MEASURED_PEAKS.json",
+            "launch_ms": k2_s * 1e3, "launch_ms_alone": k2_alone_ms, "launches_timed": k2_n,
+            "launch_ms_in_graph": k2_graph_ms,
+            "frac_in_graph": (ops / (k2_graph_ms * 1e-3)) / (2.0 * sad_peak) if k2_graph_ms else None,
+        }
+    roofline.update({
         "step_timeline_us": {k: [round(x, 2) for x in v] if isinstance(v, tuple) else round(v, 2)
                              for k, v in tl.items()},
         "hbm_achieved_gbs": alg_bytes / k2_s / 1e9, "hbm_peak_gbs": hbm_peak,
         "hbm_frac": alg_bytes / k2_s / 1e9 / hbm_peak,
         "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
         "traffic": None,
-    }
+    })
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
         with open(os.path.join(ROOT, "profiles", "k2_traffic.json")) as f:
             tr = json.load(f)

@@ -222,12 +222,32 @@ int nvb_debug_step_clocks(nvb_engine *e, long long *out);
  * out [4][2048][3], ns, of the last step-batch; 0 = CTA not present. */
 int nvb_debug_timeline(nvb_engine *e, int nsteps, long long *out);
 
+/* Which distance kernel scores the glimpses.  mode 0 (default): the tensor-core kernel
+ * (tcgen05 int8, exact thermometer form of the sum of absolute differences) whenever the V
+ * quantisation has at most 9 levels, chem_weight is 0 and the batch has at least 96
+ * glimpses, else the byte-SIMD kernel; mode 1: the byte-SIMD kernel everywhere.  Both give
+ * the same integer minima and view indices. */
+int nvb_set_distance_kernel(nvb_engine *e, int mode);
+/* 1 if the current agent batch is scored by the tensor-core kernel, else 0. */
+int nvb_distance_kernel(nvb_engine *e);
+
+/* Test hook: sin and cos of n host doubles as the device-resident stepping loop computes
+ * them (csrc/glibc_trig.cuh: the GNU C Library's algorithm, so that positions match the
+ * reference's host trigonometry bit for bit, NavBySceneFamiliarity.py:319-320). */
+int nvb_debug_sincos(nvb_engine *e, const double *x, int64_t n, double *s, double *c);
+
 /* Counters for bench.py: kernels launched by this engine so far. */
 int64_t nvb_launch_count(nvb_engine *e);
 /* Integer byte-SIMD issue-rate probe (register-resident VABSDIFF4+accumulate
  * loop on every SM); returns pixel-compares per second, the denominator of
  * the distance kernel's ALU roofline. */
 double nvb_probe_sad_peak(nvb_engine *e, int iters);
+/* int8 tensor-core issue-rate probe (tcgen05.mma kind::i8, 128 x 256 x 32 tiles on operands
+ * resident in shared memory, one CTA per SM); returns integer operations (2 per multiply-add)
+ * per second: the denominator of the tensor-core distance kernel's roofline. */
+double nvb_probe_mma_peak(nvb_engine *e, int iters);
+/* Thermometer planes the V quantisation needs (0: the tensor-core kernel does not apply). */
+int nvb_tc_planes(nvb_engine *e);
 /* Device time of the distance kernel alone on the current agent batch
  * (CUDA events on the engine stream, `reps` launches); milliseconds/launch. */
 double nvb_time_distance_kernel(nvb_engine *e, int reps);

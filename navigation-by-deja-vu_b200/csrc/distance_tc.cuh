@@ -319,23 +319,64 @@ k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensor
 }
 
 // ---- operand encoding ---------------------------------------------------------------
-// src [rows][Ppad] uint8 (quantised V plane) -> dst [rows][Kpad] int8, k = plane * P + p;
-// glimpse side (IS_A): +-w_k, library side: +-1.  Bytes k >= planes * P stay zero (the
-// buffer is zeroed once when it is allocated).  level_of[v] = index of v among the levels.
+// src [rows][Ppad] uint8 (quantised V plane) -> dst [rows][Kpad] int8, pixel-major:
+// k = p * n_planes + plane; glimpse side (IS_A): +-w_k, library side: +-1.  Bytes
+// k >= n_planes * P stay zero (the buffer is zeroed once when it is allocated).
+// level_of[v] = index of the quantised value v among the levels, level_of[256 + v] = 1 if v
+// is one of the levels; a value that is not (a library or a query uploaded from the host that
+// was not produced by this sensor's quantisation) sets *bad: the caller then falls back to the
+// byte-SIMD kernel, which takes any bytes.
+// (In the stepping loop the sampler writes the glimpse side itself, sampler.cuh.)
 template <bool IS_A>
 __global__ void k_tc_encode(const uint8_t *src, long long rows, int P, int Ppad, int Kpad, TcPlanes pl,
-                            const uint8_t *level_of, int8_t *dst)
+                            const uint8_t *level_of, int8_t *dst, int *bad)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * P) return;
     const long long r = i / P;
     const int p = (int)(i - r * P);
-    const int lvl = level_of[src[(size_t)r * Ppad + p]];
-    int8_t *o = dst + (size_t)r * Kpad + p;
+    const int v = src[(size_t)r * Ppad + p];
+    const int lvl = level_of[v];
+    if (!level_of[256 + v]) *bad = 1;
+    int8_t *o = dst + (size_t)r * Kpad + (size_t)p * pl.n_planes;
 #pragma unroll
     for (int k = 0; k < NVB_TC_MAX_PLANES; k++)
         if (k < pl.n_planes) {
             const int sgn = (lvl > (int)pl.thr_level[k]) ? 1 : -1;
-            o[(size_t)k * P] = (int8_t)(IS_A ? sgn * (int)pl.weight[k] : sgn);
+            o[k] = (int8_t)(IS_A ? sgn * (int)pl.weight[k] : sgn);
         }
+}
+
+// int8 tensor-core issue-rate probe (bench.py's roofline denominator for k2_tc, next to the
+// measured bf16 figure of MEASURED_PEAKS.json): every CTA (one per SM) issues `iters` x 4
+// back-to-back 128 x 256 x 32 MMAs on operands that stay in shared memory.
+#define NVB_PROBE_UMMA_SMEM (16384 + 32768 + 1024)
+__global__ void __launch_bounds__(128, 1) k_probe_umma(int iters)
+{
+    extern __shared__ uint8_t smem_probe_raw[];
+    uint8_t *smem = smem_probe_raw + ((1024u - (nvb_smem_u32(smem_probe_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x01FF01FFu * (uint32_t)(i & 3);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's reads
+    if (tid == 0) { nvb_mbar_init(&bar, 1); nvb_fence_barrier_init(); }
+    if (tid < 32) nvb_tmem_alloc(&slot, 512);
+    nvb_tc_fence_before();
+    __syncthreads();
+    nvb_tc_fence_after();
+    const uint32_t tmem_base = slot;
+    if (tid == 0) {
+        constexpr uint32_t idesc = nvb_umma_idesc_i8(128, 256);
+        const uint64_t da = nvb_umma_desc<128>(smem), db = nvb_umma_desc<128>(smem + 16384);
+        for (int it = 0; it < iters; it++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                nvb_umma_i8(tmem_base + (uint32_t)((it & 1) * 256), da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, 1u);
+        nvb_umma_commit(&bar);
+        nvb_mbar_wait(&bar, 0);
+    }
+    nvb_tc_fence_before();
+    __syncthreads();
+    if (tid < 32) nvb_tmem_dealloc(tmem_base, 512);
 }

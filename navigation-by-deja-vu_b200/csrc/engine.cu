@@ -18,6 +18,7 @@
 #include "../../include/navsim_b200.h"
 #include "common.cuh"
 #include "distance.cuh"
+#include "distance_tc.cuh"
 #include "sampler.cuh"
 #include "step.cuh"
 
@@ -93,6 +94,21 @@ struct nvb_engine {
     int steps_done = 0;
     int *d_spans = nullptr;         // per-CTA unit spans of the distance kernel
     int span_key[4] = {-1, -1, -1, -1};
+    // tensor-core distance kernel (distance_tc.cuh): thermometer planes of the V quantisation,
+    // encoded glimpses / library and their tensor maps
+    bool tc_ok = false;             // the V quantisation has few enough levels (<= NVB_TC_MAX_PLANES planes)
+    bool tc_off = false;            // nvb_set_distance_kernel(e, 1): byte-SIMD kernel everywhere
+    TcPlanes tc_planes{};
+    int tc_K = 0, tc_Kpad = 0, tc_kch = 0, tc_sad_const = 0;
+    uint8_t *d_tc_tab = nullptr;    // sampler tables (SamplerArgs::tc_tab)
+    uint8_t *d_tc_level_of = nullptr;   // [256] quantised value -> level index, [256] is-a-level flags (k_tc_encode)
+    int *d_tc_bad = nullptr;            // set by k_tc_encode when it meets a value that is not a level
+    bool tc_lib_ok = false;             // the library holds level values only (checked when it is encoded)
+    int8_t *d_genc = nullptr, *d_lenc = nullptr;
+    bool lenc_valid = false;
+    CUtensorMap tm_genc, tm_lenc;
+    int *d_spans_tc = nullptr;
+    int span_tc_key[3] = {-1, -1, -1};
     // view-sharded library over NVLink peer memory
     P2PArea *d_xarea = nullptr;
     P2PArgs p2p{};
@@ -256,6 +272,138 @@ static int rebuild_tmap(nvb_engine *e)
     return NVB_OK;
 }
 
+static PFN_tmapEncodeTiled tmap_encoder()
+{
+    static PFN_tmapEncodeTiled encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            fn && qres == cudaDriverEntryPointSuccess)
+            encode = (PFN_tmapEncodeTiled)fn;
+    }
+    return encode;
+}
+
+// ---- tensor-core distance kernel: operand planes, buffers, tensor maps ---------------------
+// NAVSIM_B200_NO_TC=1 keeps every configuration on the byte-SIMD kernel (k2_sad_v).
+#define NVB_TC_MIN_G 96   /* fewer glimpses than this leave most of a 128-row MMA tile empty */
+
+static bool use_tc(const nvb_engine *e, long long G)
+{
+    static const bool off = getenv("NAVSIM_B200_NO_TC") != nullptr;
+    return e->tc_ok && !e->tc_off && e->cw == 0.0 && G >= NVB_TC_MIN_G && !off;
+}
+
+// Thermometer planes of the V-channel quantisation table (distance_tc.cuh): levels = the
+// distinct table values plus 0 (masked pixels are 0 whatever the table says), one plane per
+// gap between consecutive levels, gaps above 127 split so that every weight fits an int8.
+static int build_tc_planes(nvb_engine *e, const uint8_t *lut_v)
+{
+    e->tc_ok = false;
+    e->lenc_valid = false;
+    bool seen[256] = {false};
+    seen[0] = true;
+    for (int x = 0; x < 256; x++) seen[lut_v[x]] = true;
+    std::vector<int> levels;
+    for (int v = 0; v < 256; v++)
+        if (seen[v]) levels.push_back(v);
+    if ((int)levels.size() > NVB_TC_TAB_LEVELS) return NVB_OK;
+    TcPlanes pl{};
+    for (size_t k = 0; k + 1 < levels.size(); k++) {
+        int w = levels[k + 1] - levels[k];
+        const int parts = (w + 126) / 127;
+        for (int q = 0; q < parts; q++) {
+            if (pl.n_planes == NVB_TC_MAX_PLANES) return NVB_OK;   // too many planes: byte-SIMD kernel
+            const int wq = w / (parts - q);
+            pl.weight[pl.n_planes] = (int8_t)wq;
+            pl.thr_level[pl.n_planes] = (uint8_t)k;
+            pl.n_planes++;
+            w -= wq;
+        }
+    }
+    if (pl.n_planes == 0) return NVB_OK;
+    uint8_t level_of[512] = {0}, tab[NVB_TC_TAB_BYTES] = {0};
+    for (size_t i = 0; i < levels.size(); i++) { level_of[levels[i]] = (uint8_t)i; level_of[256 + levels[i]] = 1; }
+    for (int v = 0; v < 256; v++) tab[v] = level_of[lut_v[v]];
+    int sum_w = 0;
+    for (int k = 0; k < pl.n_planes; k++) sum_w += pl.weight[k];
+    for (size_t l = 0; l < levels.size(); l++)
+        for (int k = 0; k < pl.n_planes; k++)
+            tab[256 + l * 8 + k] = (uint8_t)(int8_t)(((int)l > (int)pl.thr_level[k]) ? pl.weight[k] : -pl.weight[k]);
+    int rc;
+    if ((rc = alloc_dev(&e->d_tc_tab, (size_t)NVB_TC_TAB_BYTES))) return rc;
+    if ((rc = alloc_dev(&e->d_tc_level_of, (size_t)512))) return rc;
+    if ((rc = alloc_dev(&e->d_tc_bad, (size_t)1))) return rc;
+    CK(cudaMemset(e->d_tc_bad, 0, sizeof(int)));
+    CK(cudaMemcpy(e->d_tc_tab, tab, sizeof tab, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_tc_level_of, level_of, sizeof level_of, cudaMemcpyHostToDevice));
+    e->tc_planes = pl;
+    e->tc_K = pl.n_planes * e->P;
+    const int k64 = nvb_round_up(e->tc_K, 64), k128 = nvb_round_up(e->tc_K, 128);
+    // 128-byte K chunks (fewer, larger TMA transactions) unless the zero padding gets heavy
+    e->tc_kch = (k128 * 4 <= e->tc_K * 5) ? 128 : 64;
+    e->tc_Kpad = e->tc_kch == 128 ? k128 : k64;
+    e->tc_sad_const = e->P * sum_w;
+    // 32-bit keys of the epilogue: 256 * |dot| + column must stay below 2^31
+    e->tc_ok = (long long)e->tc_sad_const * 256 + 256 < (1ll << 31) && tmap_encoder() != nullptr;
+    return NVB_OK;
+}
+
+static int make_tc_map(CUtensorMap *m, void *base, long long rows, int Kpad, int kch, int box_rows)
+{
+    cuuint64_t gdim[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)Kpad};
+    cuuint32_t box[2] = {(cuuint32_t)kch, (cuuint32_t)box_rows};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = tmap_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estride,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                kch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NVB_E_CUDA, "cuTensorMapEncodeTiled (operand planes) failed: %d", (int)r);
+    return NVB_OK;
+}
+
+#define NVB_TC_NT 256   /* views per MMA tile (UMMA N) */
+
+// Encoded glimpse buffer for Gcap glimpses (zeroed: the K padding must be 0) + its tensor map.
+static int ensure_tc_glimpses(nvb_engine *e, long long Gcap)
+{
+    if (!e->tc_ok) return NVB_OK;
+    int rc;
+    const size_t bytes = (size_t)Gcap * e->tc_Kpad;
+    if ((rc = alloc_dev(&e->d_genc, bytes))) return rc;
+    CK(cudaMemsetAsync(e->d_genc, 0, bytes, e->stream));
+    return make_tc_map(&e->tm_genc, e->d_genc, Gcap, e->tc_Kpad, e->tc_kch, NVB_TC_TM);
+}
+
+// Encoded library (built on first use: a 10^6-view library scored by a handful of glimpses
+// never needs it).
+static int ensure_tc_library(nvb_engine *e)
+{
+    if (e->lenc_valid) return NVB_OK;
+    int rc;
+    const size_t bytes = (size_t)e->N * e->tc_Kpad;
+    if ((rc = alloc_dev(&e->d_lenc, bytes))) return rc;
+    CK(cudaMemsetAsync(e->d_lenc, 0, bytes, e->stream));
+    CK(cudaMemsetAsync(e->d_tc_bad, 0, sizeof(int), e->stream));
+    const long long n = (long long)e->N * e->P;
+    k_tc_encode<false><<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->d_lv, e->N, e->P, e->Ppad, e->tc_Kpad,
+                                                                            e->tc_planes, e->d_tc_level_of, e->d_lenc,
+                                                                            e->d_tc_bad);
+    e->launches++;
+    CK(cudaGetLastError());
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, e->d_tc_bad, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->tc_lib_ok = (bad == 0);   // a library uploaded from the host with other values: byte-SIMD kernel
+    if (!e->tc_lib_ok) { free_dev(e->d_lenc); e->d_lenc = nullptr; }
+    else if ((rc = make_tc_map(&e->tm_lenc, e->d_lenc, e->N, e->tc_Kpad, e->tc_kch, NVB_TC_NT))) return rc;
+    e->lenc_valid = true;
+    e->graph_dirty = true;
+    return NVB_OK;
+}
+
 static int ensure_glimpse_cap(nvb_engine *e, long long G)
 {
     if (G <= e->Gcap) return NVB_OK;
@@ -276,6 +424,7 @@ static int ensure_glimpse_cap(nvb_engine *e, long long G)
     if ((rc = alloc_dev(&e->d_tie_next, (size_t)G))) return rc;
     if ((rc = alloc_dev(&e->d_tie_ready, (size_t)G))) return rc;
     CK(cudaMemsetAsync(e->d_tie_ready, 0, sizeof(int) * (size_t)G, e->stream));
+    if ((rc = ensure_tc_glimpses(e, G))) return rc;
     e->Gcap = G;
     return NVB_OK;
 }
@@ -334,7 +483,8 @@ extern "C" void nvb_engine_destroy(nvb_engine *e)
                     e->d_tie_items, e->d_tie_thr, e->d_tie_next, e->d_tie_ready, e->ag.poses, e->ag.status, e->ag.completed,
                     e->ag.budget, e->ag.nav_frames, e->ag.err_sum, e->ag.err_n, e->ag.coverage,
                     e->ag.stepped, e->d_step, e->log_best, e->log_pose, e->log_sfam, e->log_afam,
-                    e->d_poses0, e->d_budget0, e->d_spans, e->d_pending, e->d_dmin2, e->d_pblk};
+                    e->d_poses0, e->d_budget0, e->d_spans, e->d_pending, e->d_dmin2, e->d_pblk,
+                    e->d_tc_tab, e->d_tc_level_of, e->d_genc, e->d_lenc, e->d_spans_tc, e->d_tc_bad};
     for (int i = 0; i < NVB_P2P_MAX_RANKS; i++)
         if (e->p2p_opened[i]) cudaIpcCloseMemHandle(e->p2p_opened[i]);
     free_dev(e->d_xarea); free_dev(e->d_p2p_seq); free_dev(e->d_p2p_err);
@@ -357,6 +507,7 @@ extern "C" int nvb_sync(nvb_engine *e)
 extern "C" int64_t nvb_launch_count(nvb_engine *e) { return e->launches; }
 
 extern "C" void *nvb_stream_handle(nvb_engine *e) { return (void *)e->stream; }
+
 
 extern "C" int nvb_set_landscape(nvb_engine *e, const uint8_t *hsv, int rows, int cols,
                                  ptrdiff_t s_row, ptrdiff_t s_col, ptrdiff_t s_chan)
@@ -415,6 +566,8 @@ extern "C" int nvb_set_sensor(nvb_engine *e, int W, int H, int pw, int ph, const
     e->have_sensor = true;
     // sensor change invalidates library and glimpse buffers
     e->N = 0; e->n_path = 0; e->Gcap = 0; e->B = 0;
+    int rc = build_tc_planes(e, lut + 512);
+    if (rc) return rc;
     return rebuild_tmap(e);
 }
 
@@ -593,9 +746,77 @@ static int launch_dist_cpr(nvb_engine *e, const DistArgs &da)
     return launch_dist_cfg<16, 4, 16, CPR>(e, da);
 }
 
-// K2 over glimpses [0, G) of the engine's glimpse buffers; keys must be reset.
-static int launch_distance(nvb_engine *e, int G, bool bump_step = false)
+template <int KCH, int STAGES>
+static int launch_tc_cfg(nvb_engine *e, TcArgs ta)
 {
+    using C = TcCfg<KCH, NVB_TC_NT, STAGES>;
+    auto kern = k2_tc<KCH, NVB_TC_NT, STAGES>;
+    static bool attr_set[64] = {false};
+    if (!attr_set[e->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set[e->device & 63] = true;
+    }
+    const int n_gt = (ta.G + C::TM - 1) / C::TM, n_vt = (ta.N + NVB_TC_NT - 1) / NVB_TC_NT;
+    const long long items = (long long)n_gt * n_vt;
+    const int n_cta = (int)(items < e->sm_count ? items : e->sm_count);
+    if (!(e->span_tc_key[0] == n_gt && e->span_tc_key[1] == n_vt && e->span_tc_key[2] == n_cta)) {
+        std::vector<int> spans(n_cta + 1);
+        const long long base = items / n_cta, rem = items % n_cta;
+        long long u = 0;
+        for (int c = 0; c < n_cta; c++) { spans[c] = (int)u; u += base + (c < rem ? 1 : 0); }
+        spans[n_cta] = (int)items;
+        int rc = alloc_dev(&e->d_spans_tc, (size_t)n_cta + 1);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(e->d_spans_tc, spans.data(), sizeof(int) * (n_cta + 1), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));   // spans is a stack vector
+        e->span_tc_key[0] = n_gt; e->span_tc_key[1] = n_vt; e->span_tc_key[2] = n_cta;
+        e->graph_dirty = true;
+    }
+    ta.n_vt = n_vt;
+    ta.kchunks = e->tc_Kpad / KCH;
+    ta.spans = e->d_spans_tc;
+    CK(launch_seq(kern, dim3((unsigned)n_cta), dim3(NVB_TC_THREADS), (size_t)C::SMEM, e->stream, e->tm_genc, e->tm_lenc, ta));
+    e->launches++;
+    CK(cudaGetLastError());
+    return NVB_OK;
+}
+
+// K2 on the tensor cores.  encode_glimpses: the glimpse planes were not written by the sampler
+// (queries uploaded from the host): encode them from the V plane first.
+static int launch_distance_tc(nvb_engine *e, int G, bool bump_step, bool encode_glimpses)
+{
+    if (encode_glimpses) {
+        const long long n = (long long)G * e->P;
+        k_tc_encode<true><<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->d_gv, G, e->P, e->Ppad, e->tc_Kpad,
+                                                                             e->tc_planes, e->d_tc_level_of, e->d_genc,
+                                                                             e->d_tc_bad);
+        e->launches++;
+        CK(cudaGetLastError());
+    }
+    TcArgs ta{};
+    ta.G = G; ta.N = e->N;
+    ta.keys = e->d_keys;
+    ta.view_offset = e->view_offset;
+    ta.sad_const = e->tc_sad_const;
+    ta.step_counter = bump_step ? e->d_step : nullptr;
+    ta.tie_count = bump_step ? e->d_tie_count : nullptr;
+    ta.pdl_early = (bump_step && early_trigger()) ? 1 : 0;
+    ta.tl = bump_step ? e->d_tl : nullptr;
+    if (e->tc_kch == 128) return launch_tc_cfg<128, 4>(e, ta);
+    return launch_tc_cfg<64, 8>(e, ta);
+}
+
+// K2 over glimpses [0, G) of the engine's glimpse buffers; keys must be reset.
+// glimpses_encoded: the sampler of the stepping loop wrote the thermometer planes as well.
+static int launch_distance(nvb_engine *e, int G, bool bump_step = false, bool glimpses_encoded = false)
+{
+    if (use_tc(e, G)) {
+        // (first use: encodes the library, outside any stream capture -- every graph is captured
+        // after one step with plain launches)
+        int rc = ensure_tc_library(e);
+        if (rc) return rc;
+        if (e->tc_lib_ok) return launch_distance_tc(e, G, bump_step, !glimpses_encoded);
+    }
     DistArgs da;
     da.gv = e->d_gv; da.gh = e->d_gh; da.gs = e->d_gs;
     da.lv = e->d_lv; da.lh = e->d_lh; da.ls = e->d_ls;
@@ -639,6 +860,23 @@ static int launch_distance(nvb_engine *e, int G, bool bump_step = false)
     case 8: return launch_dist_cpr<8>(e, da);
     }
     return fail(NVB_E_INVALID, "unsupported chunk count %d", e->cpr);
+}
+
+extern "C" int nvb_set_distance_kernel(nvb_engine *e, int mode)
+{
+    if (mode != 0 && mode != 1) return fail(NVB_E_INVALID, "mode must be 0 (automatic) or 1 (byte SIMD)");
+    if (e->tc_off != (mode == 1)) e->graph_dirty = true;
+    e->tc_off = (mode == 1);
+    e->glimpses_pending = false;   // glimpses sampled ahead may lack the operand planes the other kernel reads
+    return NVB_OK;
+}
+
+extern "C" int nvb_distance_kernel(nvb_engine *e)
+{
+    if (e->B <= 0 || e->N <= 0 || !use_tc(e, (long long)e->B * e->A)) return 0;
+    if (cudaSetDevice(e->device) != cudaSuccess) return 0;
+    if (ensure_tc_library(e) != NVB_OK) return 0;
+    return e->tc_lib_ok ? 1 : 0;
 }
 
 __global__ void k_fill_u64(unsigned long long *p, long long n, unsigned long long v)
@@ -723,6 +961,7 @@ static int sample_poses(nvb_engine *e, const double *poses, const double *cs, in
     sa.band = sampler_band(e);
     sa.dbg = nullptr;
     sa.poses_src = nullptr; sa.poses_dst = nullptr; sa.pending_clear = nullptr;
+    sa.genc = nullptr; sa.tc_tab = nullptr; sa.Kpad = 0; sa.n_planes = 0;
     int rc = launch_sampler(e, sa, G);
     CK(cudaStreamSynchronize(e->stream));
     cudaFree(d_poses);
@@ -774,6 +1013,7 @@ static int alloc_library(nvb_engine *e, int N)
     e->N = N;
     e->view_offset = 0;
     e->n_total = N;
+    e->lenc_valid = false;
     return NVB_OK;
 }
 
@@ -952,11 +1192,29 @@ extern "C" int nvb_familiarity_min(nvb_engine *e, const uint8_t *scenes_q, int G
     int rc = upload_queries(e, scenes_q, G);
     if (rc) return rc;
     if ((rc = fill_u64(e, e->d_keys, G, KEY_NONE))) return rc;
-    if ((rc = launch_distance(e, G))) return rc;
     std::vector<unsigned long long> keys(G);
-    CK(cudaMemcpyAsync(keys.data(), e->d_keys, sizeof(unsigned long long) * G, cudaMemcpyDeviceToHost,
-                       e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const bool tc = attempt == 0 && use_tc(e, G);
+        if (tc) CK(cudaMemsetAsync(e->d_tc_bad, 0, sizeof(int), e->stream));
+        if (tc) {
+            if ((rc = launch_distance(e, G))) return rc;
+        } else {
+            // byte-SIMD kernel: any byte values
+            const bool ok = e->tc_ok;
+            e->tc_ok = false;
+            rc = launch_distance(e, G);
+            e->tc_ok = ok;
+            if (rc) return rc;
+        }
+        int bad = 0;
+        if (tc) CK(cudaMemcpyAsync(&bad, e->d_tc_bad, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(keys.data(), e->d_keys, sizeof(unsigned long long) * G, cudaMemcpyDeviceToHost,
+                           e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (!bad) break;
+        // a query held a value this sensor's quantisation cannot produce: score again without the planes
+        if ((rc = fill_u64(e, e->d_keys, G, KEY_NONE))) return rc;
+    }
     const int ib = (e->cw == 0.0) ? 32 : 28;
     for (int g = 0; g < G; g++) {
         const unsigned long long score = keys[g] >> ib;
@@ -1121,6 +1379,10 @@ static SamplerArgs agent_sampler_args(nvb_engine *e)
     sa.band = sampler_band(e);
     sa.dbg = e->d_dbg;
     sa.poses_src = e->zc_in; sa.poses_dst = e->ag.poses; sa.pending_clear = e->d_pending;
+    const bool tc = use_tc(e, (long long)e->B * e->A) && (!e->lenc_valid || e->tc_lib_ok);
+    sa.genc = tc ? e->d_genc : nullptr;
+    sa.tc_tab = tc ? e->d_tc_tab : nullptr;
+    sa.Kpad = e->tc_Kpad; sa.n_planes = e->tc_planes.n_planes;
     return sa;
 }
 
@@ -1289,7 +1551,7 @@ static int check_step_ready(nvb_engine *e, int fake)
 // K2 with optional event timing around it
 static int launch_distance_timed(nvb_engine *e, int G)
 {
-    if (!e->timing) return launch_distance(e, G, true);
+    if (!e->timing) return launch_distance(e, G, true, true);
     if (e->ev_used + 2 > e->ev_pool.size()) {
         for (int i = 0; i < 64; i++) {
             cudaEvent_t ev;
@@ -1298,7 +1560,7 @@ static int launch_distance_timed(nvb_engine *e, int G)
         }
     }
     CK(cudaEventRecord(e->ev_pool[e->ev_used], e->stream));
-    int rc = launch_distance(e, G, true);
+    int rc = launch_distance(e, G, true, true);
     CK(cudaEventRecord(e->ev_pool[e->ev_used + 1], e->stream));
     e->ev_used += 2;
     return rc;
@@ -1836,6 +2098,53 @@ extern "C" double nvb_probe_sad_peak(nvb_engine *e, int iters)
     return (double)grid * threads * (double)iters * 32.0 * 4.0 / (ms * 1e-3);
 }
 
+__global__ void k_debug_sincos(const double *x, long long n, double *s, double *c)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) nvb_glibc_sincos(x[i], s + i, c + i);
+}
+
+// Test hook: the device's sin / cos (csrc/glibc_trig.cuh) of n host doubles.
+extern "C" int nvb_debug_sincos(nvb_engine *e, const double *x, int64_t n, double *s, double *c)
+{
+    if (n <= 0) return NVB_OK;
+    CK(cudaSetDevice(e->device));
+    double *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double) * 3 * (size_t)n));
+    CK(cudaMemcpyAsync(d, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    k_debug_sincos<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(d, n, d + n, d + 2 * n);
+    e->launches++;
+    CK(cudaMemcpyAsync(s, d + n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(c, d + 2 * n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d);
+    return NVB_OK;
+}
+
+extern "C" double nvb_probe_mma_peak(nvb_engine *e, int iters)
+{
+    if (cudaSetDevice(e->device) != cudaSuccess || iters <= 0) return -1.0;
+    if (cudaFuncSetAttribute(k_probe_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, NVB_PROBE_UMMA_SMEM) != cudaSuccess)
+        return -1.0;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    k_probe_umma<<<e->sm_count, 128, NVB_PROBE_UMMA_SMEM, e->stream>>>(iters);   // warm-up
+    cudaEventRecord(t0, e->stream);
+    k_probe_umma<<<e->sm_count, 128, NVB_PROBE_UMMA_SMEM, e->stream>>>(iters);
+    cudaEventRecord(t1, e->stream);
+    e->launches += 2;
+    cudaStreamSynchronize(e->stream);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    if (ms <= 0 || cudaGetLastError() != cudaSuccess) return -1.0;
+    return (double)e->sm_count * (double)iters * 4.0 * (2.0 * 128.0 * 256.0 * 32.0) / (ms * 1e-3);
+}
+
+extern "C" int nvb_tc_planes(nvb_engine *e) { return e->tc_ok ? e->tc_planes.n_planes : 0; }
+
 extern "C" double nvb_time_distance_kernel(nvb_engine *e, int reps)
 {
     if (e->B <= 0 || e->N <= 0 || reps <= 0) return -1.0;
@@ -1845,13 +2154,13 @@ extern "C" double nvb_time_distance_kernel(nvb_engine *e, int reps)
     cudaEventCreate(&t0);
     cudaEventCreate(&t1);
     fill_u64(e, e->d_keys, G, KEY_NONE);
-    launch_distance(e, G);
+    launch_distance(e, G, false, false);   // (re-)encodes the glimpse planes from the V plane when the tensor-core kernel runs
     cudaStreamSynchronize(e->stream);
     float total = 0;
     for (int r = 0; r < reps; r++) {
         fill_u64(e, e->d_keys, G, KEY_NONE);
         cudaEventRecord(t0, e->stream);
-        launch_distance(e, G);
+        launch_distance(e, G, false, true);
         cudaEventRecord(t1, e->stream);
         cudaStreamSynchronize(e->stream);
         float ms = 0;

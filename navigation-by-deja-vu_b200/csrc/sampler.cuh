@@ -13,6 +13,7 @@
 // to global memory.  Output: planar glimpses gv/gh/gs [G][Ppad].
 #pragma once
 #include "common.cuh"
+#include "glibc_trig.cuh"
 
 struct SamplerArgs {
     NvbWorld w;
@@ -35,7 +36,17 @@ struct SamplerArgs {
     const double *poses_src;
     double *poses_dst;
     int32_t *pending_clear;
+    // tensor-core distance kernel (distance_tc.cuh): the sampler also writes the thermometer
+    // encoding of every glimpse, genc [B*A][Kpad] int8, pixel-major (k = p * n_planes + plane);
+    // tc_tab = {[256] raw block mean -> level index, [NVB_TC_TAB_LEVELS][8] level -> the
+    // glimpse-side bytes +-w_k}.  genc == nullptr: not wanted.
+    int8_t *genc;
+    const uint8_t *tc_tab;
+    int Kpad, n_planes;
 };
+
+#define NVB_TC_TAB_LEVELS 16
+#define NVB_TC_TAB_BYTES (256 + NVB_TC_TAB_LEVELS * 8)
 
 #define NVB_SAMPLER_THREADS 256
 #define NVB_PTAB_MAX 256   /* sensors of up to this many pixels keep a per-pixel origin table in shared memory */
@@ -44,8 +55,9 @@ struct SamplerArgs {
 __host__ __device__ inline size_t nvb_sampler_smem(int BW, int BH, int nplanes, int A)
 {
     size_t win = (size_t)nvb_round_up(BW * BH, 128) * (size_t)nplanes;
-    // + rotations (FP64 and FP32), heading offsets, mbarrier, quantisation tables, pixel table
-    return win + (size_t)A * 32 + 64 + 768 + NVB_PTAB_MAX * 8;
+    // + rotations (FP64 and FP32), heading offsets, mbarrier, quantisation tables, pixel table,
+    // thermometer tables of the tensor-core distance kernel (256 + 16 * 8 bytes)
+    return win + (size_t)A * 32 + 64 + 768 + NVB_PTAB_MAX * 8 + 384;
 }
 
 // Sample coordinates (util.pyx:159-168).  The reference evaluates
@@ -172,6 +184,14 @@ __device__ __forceinline__ void nvb_sampler_stage_ptab(const NvbWorld &w, float2
     }
 }
 
+// Thermometer tables of the tensor-core distance kernel -> shared memory (constant per world).
+__device__ __forceinline__ void nvb_sampler_stage_tc(const uint8_t *tc_tab, uint8_t *tc_sm)
+{
+    if (tc_tab == nullptr) return;
+    for (int k = threadIdx.x; k < NVB_TC_TAB_BYTES / 4; k += blockDim.x)
+        reinterpret_cast<uint32_t *>(tc_sm)[k] = __ldg(reinterpret_cast<const uint32_t *>(tc_tab) + k);
+}
+
 // Shared-memory layout of one sampling CTA (dynamic shared memory, nvb_sampler_smem bytes).
 struct SamplerSmem {
     uint8_t *win_v, *win_h, *win_s;   // staged window planes
@@ -182,6 +202,7 @@ struct SamplerSmem {
     double *offs;                     // [A] heading offsets (staged by kernels that want them close)
     float2 *ptab;                     // [P <= NVB_PTAB_MAX] sensor pixel -> (px0, py0), its block's origin
     int *err;                         // IndexError flag of this CTA
+    uint8_t *tc;                      // [NVB_TC_TAB_BYTES] thermometer tables (SamplerArgs::tc_tab), 8-byte aligned
 };
 
 template <bool NEED_HS>
@@ -200,6 +221,7 @@ __device__ __forceinline__ SamplerSmem nvb_sampler_layout(const NvbWorld &w, int
     L.offs = (double *)(L.csf + A);
     L.ptab = (float2 *)(L.offs + A);
     L.err = (int *)(L.ptab + NVB_PTAB_MAX);
+    L.tc = (uint8_t *)(L.err + 2);
     return L;
 }
 
@@ -254,7 +276,7 @@ __device__ __forceinline__ void nvb_sample_rotations(const SamplerArgs &a, int b
             double angle = ang;
             if (a.agent_mode) angle = nvb_pymod_pos(__dadd_rn(ang, offsets[k]), NVB_TWO_PI);
             double rot = -__dsub_rn(0.5 * NVB_PI, angle);
-            sincos(rot, &s, &c);
+            nvb_glibc_sincos(rot, &s, &c);   // the host libm's bits (util.pyx:144-145 call libc cos / sin)
         }
         L.cs[2 * k] = c;
         L.cs[2 * k + 1] = s;
@@ -283,6 +305,7 @@ __device__ __forceinline__ void nvb_sample_body(const CUtensorMap *tmap, const S
     if (!LUT_STAGED) {
         nvb_sampler_stage_lut(a.w, L.lut);
         nvb_sampler_stage_ptab(a.w, L.ptab);
+        nvb_sampler_stage_tc(a.genc != nullptr ? a.tc_tab : nullptr, L.tc);
     }
     nvb_sample_rotations(a, b, ang, L, a.offsets, 0, (int)blockDim.x, k0, k1);
     nvb_sample_gather<NEED_HS, PH, PW>(a, b, x, y, L, fail_out, k0, k1);
@@ -423,6 +446,17 @@ __device__ __forceinline__ void nvb_sample_gather(const SamplerArgs &a, int b, d
         const bool masked = (px0 >= mask_lo && px0 < mask_hi);
         const size_t o = out0 + (linear_out ? (size_t)it : (size_t)k * w.Ppad + p);
         a.gv[o] = masked ? 0 : lut_sm[512 + v];
+        if (a.genc != nullptr) {
+            // the same pixel as +-w_k thermometer bytes for the tensor-core distance kernel
+            const int lvl = masked ? 0 : (int)L.tc[v];
+            const uint8_t *enc = L.tc + 256 + lvl * 8;
+            int8_t *eo = a.genc + ((size_t)b * a.A + k) * a.Kpad + (size_t)p * a.n_planes;
+            if (a.n_planes == 4) {
+                *reinterpret_cast<uint32_t *>(eo) = *reinterpret_cast<const uint32_t *>(enc);
+            } else {
+                for (int q = 0; q < a.n_planes; q++) eo[q] = (int8_t)enc[q];
+            }
+        }
         if (NEED_HS) {
             // util.pyx:126-132: hue with the largest summed S (strict >, so the
             // lowest hue wins ties and hue 0 wins when every sum is 0);

@@ -386,7 +386,7 @@ __device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigne
         if (tid == 0) {
             const double ang = nvb_pymod_pos(__dadd_rn(pre.ang0, offsets[best]), NVB_TWO_PI);   // :317
             double sn, cs;
-            sincos(ang, &sn, &cs);
+            nvb_glibc_sincos(ang, &sn, &cs);   // np.cos / np.sin = glibc's (:319-320)
             const double x = __dadd_rn(pre.px, __dmul_rn(a.step_size, cs));   // :319
             const double y = __dadd_rn(pre.py, __dmul_rn(a.step_size, sn));   // :320
             s_pose[0] = x; s_pose[1] = y; s_pose[2] = ang;
@@ -903,6 +903,7 @@ k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs
     // shared memory, the training path (every CTA of the SM scans all of it) -> L1
     nvb_sampler_stage_lut(sa.w, L.lut);
     nvb_sampler_stage_ptab(sa.w, L.ptab);
+    nvb_sampler_stage_tc(sa.genc != nullptr ? sa.tc_tab : nullptr, L.tc);
     for (int k = threadIdx.x; k < a.A; k += blockDim.x) L.offs[k] = a.offsets[k];
     if (a.pblk != nullptr) {   // update_error reads the block bounds of the whole path, then a few blocks
         const int bytes = ((a.n_path + NVB_PATH_BLOCK - 1) / NVB_PATH_BLOCK) * 32;

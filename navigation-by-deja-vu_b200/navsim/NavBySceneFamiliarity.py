@@ -122,6 +122,7 @@ class NavBySceneFamiliarity(object):
         self.step_familiarity = np.inf
         self.max_distance_to_training_path = max_distance_to_training_path
         self._ahead = None
+        self.replay_restarts = 0      # run-aheads recomputed because the device and the host bookkeeping disagreed
         self.clear_training()
         self.reset_error()
 
@@ -239,24 +240,28 @@ class NavBySceneFamiliarity(object):
         return self._scene_familiarity
 
     # ---- stepping -----------------------------------------------------------
+    def _nav_params(self):
+        """The plain attributes the reference reads at every step (:263,271,328): the caller may
+        change them between steps, which invalidates a run-ahead computed with the old values."""
+        return (self.max_distance_to_training_path, self.step_size, self.threshold_factor,
+                self.coverage_threshold_factor)
+
     def _run_ahead(self, fake):
         e = self._engine
-        e.max_distance_to_training_path = self.max_distance_to_training_path
-        e.step_size = self.step_size
-        e.threshold_factor = self.threshold_factor
-        e.coverage_threshold_factor = self.coverage_threshold_factor
+        (e.max_distance_to_training_path, e.step_size, e.threshold_factor,
+         e.coverage_threshold_factor) = params = self._nav_params()
         e.set_agents([(self._position[0], self._position[1], self._angle)])
         n = 1 if fake else RUN_AHEAD_STEPS
         e.step(n, fake=fake, log_afam=True)
         log = e.log(0, n, afam=True)
         st = e.state(coverage=False)
-        self._ahead = dict(i=0, n=n, log=log, status=int(st["status"][0]), fake=fake)
+        self._ahead = dict(i=0, n=n, log=log, status=int(st["status"][0]), fake=fake, params=params)
 
     def step_forward(self, fake=False):
         if self.training_path is None:
             raise TypeError("'NoneType' object is not callable")   # untrained, as in the reference
         ah = self._ahead
-        if ah is None or ah["i"] >= ah["n"] or ah["fake"] != bool(fake):
+        if ah is None or ah["i"] >= ah["n"] or ah["fake"] != bool(fake) or ah["params"] != self._nav_params():
             self._run_ahead(bool(fake))
             ah = self._ahead
         i = ah["i"]
@@ -274,8 +279,14 @@ class NavBySceneFamiliarity(object):
                 raise OutOfLandscapeBoundsException()
             if status == _cabi.INDEX_ERROR:
                 raise IndexError("Index out of bounds (axis 0)")
-            # the device stopped where the host bookkeeping did not (a last-bit
-            # difference at a threshold): restart the run-ahead from the host state
+            # The device stopped this agent (too far / end of path) at a step where the host-side
+            # bookkeeping below did not.  Positions are bit-identical, so this needs a threshold
+            # compared differently in the last bit (np.linalg.norm's BLAS dot may fuse where the
+            # kernel does not, :328): the host state is the reference's, so the run-ahead is
+            # recomputed from it -- counted, never silent.
+            self.replay_restarts += 1
+            if self.replay_restarts > 8 + self.navigated_for_frames:
+                raise RuntimeError("device log and host bookkeeping keep disagreeing (status %d)" % status)
             self._run_ahead(bool(fake))
             return self.step_forward(fake)
         self.angle_familiarity[:] = log["afam"][i, 0]

@@ -55,10 +55,15 @@ SIGNATURES = {
     "nvb_p2p_attach": (_i, [_vp, _i, _i, _vp]),
     "nvb_p2p_error": (_i, [_vp]),
     "nvb_device_ptr": (_vp, [_vp, _i]),
+    "nvb_debug_sincos": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "nvb_debug_step_clocks": (_i, [_vp, _vp]),
     "nvb_debug_timeline": (_i, [_vp, _i, _vp]),
+    "nvb_set_distance_kernel": (_i, [_vp, _i]),
+    "nvb_distance_kernel": (_i, [_vp]),
     "nvb_launch_count": (_i64, [_vp]),
     "nvb_probe_sad_peak": (_d, [_vp, _i]),
+    "nvb_probe_mma_peak": (_d, [_vp, _i]),
+    "nvb_tc_planes": (_i, [_vp]),
     "nvb_time_distance_kernel": (_d, [_vp, _i]),
 }
 

@@ -269,6 +269,15 @@ class NavEngine(object):
     def set_options(self, use_graph=True, kernel_timing=False):
         check(self._lib.nvb_set_options(self._h, int(bool(use_graph)), int(bool(kernel_timing))))
 
+    def set_distance_kernel(self, simd_only=False):
+        """False (default): tensor-core distance kernel where it applies; True: byte SIMD everywhere."""
+        check(self._lib.nvb_set_distance_kernel(self._h, int(bool(simd_only))))
+
+    @property
+    def distance_kernel(self):
+        """Name of the kernel that scores the current agent batch."""
+        return "k2_tc" if self._lib.nvb_distance_kernel(self._h) else ("k2_sad_hsv" if self.chem_weight else "k2_sad_v")
+
     def kernel_time_ms(self):
         """(summed ms, launches) of the distance kernel since set_options(kernel_timing=True)."""
         n = C.c_int64(0)
@@ -357,6 +366,20 @@ class NavEngine(object):
     def probe_sad_peak(self, iters=4096):
         return float(self._lib.nvb_probe_sad_peak(self._h, int(iters)))
 
+    def device_sincos(self, x):
+        """(sin, cos) of a float64 array as the stepping loop computes them on the device."""
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        s, c = np.empty_like(x), np.empty_like(x)
+        check(self._lib.nvb_debug_sincos(self._h, ptr(x), len(x), ptr(s), ptr(c)))
+        return s, c
+
+    def probe_mma_peak(self, iters=2048):
+        return float(self._lib.nvb_probe_mma_peak(self._h, int(iters)))
+
+    @property
+    def tc_planes(self):
+        return int(self._lib.nvb_tc_planes(self._h))
+
     def time_distance_kernel(self, reps=20):
         return float(self._lib.nvb_time_distance_kernel(self._h, int(reps)))
 
@@ -366,7 +389,7 @@ class NavEngine(object):
         since the step-batch's first stamp, plus 'span' = the whole step-batch."""
         out = np.zeros((4, 2048, 3), np.int64)
         check(self._lib.nvb_debug_timeline(self._h, int(nsteps), ptr(out)))
-        names = ["k2_sad_v", "k3_decide", "k3_ties", "k3_move_sample"]
+        names = ["k2", "k3_decide", "k3_ties", "k3_move_sample"]
         res = {}
         t0 = None
         for k, name in enumerate(names):

@@ -156,3 +156,35 @@ def test_scene_familiarity_values(gpu, name):
         assert got.shape == sf.shape
         assert np.array_equal(got, sf), (name, f)
         assert np.allclose(nsf.angle_familiarity, af, rtol=FAM_RTOL, atol=0)
+
+
+def test_dropin_parameters_changed_mid_run(gpu):
+    """max_distance_to_training_path is a plain attribute the reference reads at every step
+    (NavBySceneFamiliarity.py:263): changing it between steps must take effect at the next step
+    even though the device has already run ahead with the old value."""
+    import navsim
+    from oracle import oracle as O
+    L, w, tpath, pose, frames = build_case("c1_small")
+    kw = dict(w)
+    kw["max_distance_to_training_path"] = 450
+    nsf = navsim.NavBySceneFamiliarity(L, familiarity_model=navsim.sads_familiarity(0.0), **kw)
+    nsf.train_from_path(tpath)
+    off = (pose[0] + 25.0, pose[1] - 25.0, pose[2] + 0.5)      # starts ~35 px off the path
+    nsf.position = off[:2]
+    nsf.angle = off[2]
+    ow = O.World(L, **kw)
+    ow.train_from_path(tpath)
+    ag = ow.new_agent(*off)
+    for _ in range(5):
+        nsf.step_forward()
+        rc, best, af, _sf = ow.step_forward(ag)
+        assert rc == 0
+    assert nsf.position == (ag.x, ag.y)
+    nsf.max_distance_to_training_path = 1.0                    # now every step is "too far"
+    ow._w.max_dist = 1.0
+    rc, best, af, _sf = ow.step_forward(ag)
+    assert rc == O.TOO_FAR
+    with pytest.raises(navsim.TooFarFromTrainingPathException):
+        nsf.step_forward()
+    assert nsf.position == (ag.x, ag.y) and nsf.navigated_for_frames == ag.navigated_for_frames
+    assert nsf.replay_restarts == 0

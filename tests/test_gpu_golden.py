@@ -7,7 +7,7 @@ from golden_util import TRAJ, primitives, trajectory
 
 pytestmark = pytest.mark.gpu
 
-POS_TOL = 1e-9    # px; device sin/cos vs glibc, DESIGN.md "trig parity"
+POS_TOL = 0.0    # px: exact -- the device computes sin / cos with glibc's own algorithm (csrc/glibc_trig.cuh)
 FAM_RTOL = 1e-12  # angle_familiarity where several views tie at a heading's minimum
 
 

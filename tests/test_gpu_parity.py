@@ -6,8 +6,8 @@ angle_familiarity is bit-exact unless several views tie at a heading's integer
 minimum, where the reference's max over doubles picks one by rounding noise
 (bound: FAM_RTOL; > 90 % of the values are checked to be bit-exact).  Headings
 that tie for the step's best integer minimum are always resolved in exact FP64
-over every tied view, so the chosen heading index is exact.  Agent positions within POS_TOL (device sin/cos vs
-glibc may differ in the last bit, DESIGN.md "trig parity").
+over every tied view, so the chosen heading index is exact.  Agent positions are bit-identical (POS_TOL = 0): the
+device's sin / cos restate glibc's algorithm (csrc/glibc_trig.cuh, tests/test_glibc_trig.py).
 """
 import numpy as np
 import pytest
@@ -16,7 +16,7 @@ from cases import CASES, agent_grid, build_case
 
 pytestmark = pytest.mark.gpu
 
-POS_TOL = 1e-9   # px, absolute
+POS_TOL = 0.0    # px: exact -- the device computes sin / cos with glibc's own algorithm (csrc/glibc_trig.cuh)
 FAM_RTOL = 1e-12  # relative, angle_familiarity of non-winning headings (north_star asks for FP32-level 1e-6)
 
 

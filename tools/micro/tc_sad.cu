@@ -115,9 +115,9 @@ static void run_tc(Ctx &c, const TcPlanes &pl, const uint8_t *d_level_of, const 
     for (int r = 0; r < c.reps + 2; r++) {
         k_fill<<<(c.G + 255) / 256, 256>>>(c.d_keys, c.G, NVB_KEY_NONE);
         CK(cudaEventRecord(e0));
-        k_tc_encode<true><<<(unsigned)(((long long)c.G * c.P + 255) / 256), 256>>>(c.d_g, c.G, c.P, c.Ppad, Kpad, pl, d_level_of, d_a);
+        k_tc_encode<true><<<(unsigned)(((long long)c.G * c.P + 255) / 256), 256>>>(c.d_g, c.G, c.P, c.Ppad, Kpad, pl, d_level_of, d_a, (int *)(d_level_of + 512));
         CK(cudaEventRecord(e1));
-        if (r == 0) k_tc_encode<false><<<(unsigned)(((long long)c.N * c.P + 255) / 256), 256>>>(c.d_l, c.N, c.P, c.Ppad, Kpad, pl, d_level_of, d_b);
+        if (r == 0) k_tc_encode<false><<<(unsigned)(((long long)c.N * c.P + 255) / 256), 256>>>(c.d_l, c.N, c.P, c.Ppad, Kpad, pl, d_level_of, d_b, (int *)(d_level_of + 512));
         CK(cudaDeviceSynchronize());
         float ms;
         CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -226,8 +226,8 @@ int main(int argc, char **argv)
         }
     }
     TcPlanes pl{};
-    std::vector<uint8_t> level_of(256, 0);
-    for (size_t i = 0; i < levels.size(); i++) level_of[levels[i]] = (uint8_t)i;
+    std::vector<uint8_t> level_of(512, 0);
+    for (size_t i = 0; i < levels.size(); i++) { level_of[levels[i]] = (uint8_t)i; level_of[256 + levels[i]] = 1; }
     for (size_t k = 0; k + 1 < levels.size(); k++) {
         int w = levels[k + 1] - levels[k];
         const int parts = (w + 126) / 127;
@@ -280,8 +280,9 @@ int main(int argc, char **argv)
     CK(cudaMemcpy(c.d_g, gl.data(), gl.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c.d_l, lib.data(), lib.size(), cudaMemcpyHostToDevice));
     uint8_t *d_level_of;
-    CK(cudaMalloc(&d_level_of, 256));
-    CK(cudaMemcpy(d_level_of, level_of.data(), 256, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_level_of, 512 + 16));
+    CK(cudaMemcpy(d_level_of, level_of.data(), 512, cudaMemcpyHostToDevice));
+    CK(cudaMemset(d_level_of + 512, 0, 16));
 
     const char *only = getenv("TC_ONLY");
     if (c.P == 80 && !only) {

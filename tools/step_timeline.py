@@ -13,7 +13,7 @@ eng.set_agents(poses)
 eng.step(20); eng.sync()
 out = np.zeros((4, 2048, 3), np.int64)
 _cabi.check(eng._lib.nvb_debug_timeline(eng._h, 12, _cabi.ptr(out)))
-names = ["k2_sad_v", "k3_decide", "k3_ties", "k3_move_sample"]
+names = ["k2", "k3_decide", "k3_ties", "k3_move_sample"]
 t0 = None
 rows = []
 for k, name in enumerate(names):

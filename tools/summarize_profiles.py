@@ -64,7 +64,7 @@ def main():
         step = {}
         for k, v in per.items():
             f.write("%-72s n=%4d mean=%8.2f us\n" % (k[:72], len(v), sum(v) / len(v)))
-            for key in ("k2_sad_v", "k3_decide", "k3_ties", "k3_move_sample"):
+            for key in ("k2", "k3_decide", "k3_ties", "k3_move_sample"):
                 if key in k:
                     step[key] = sum(v) / len(v)
         tot = sum(step.values())
