@@ -379,8 +379,15 @@ def run_ours(args):
 # --------------------------------------------------------------------------- CPU arm
 def _cpu_worker(argv):
     """One process = a few agents of the workload, stepped one after another
-    (what `mpirun -n cores` over independent trials does, run_experiment.py:327)."""
-    wl, my_poses, warm, steps, use_ref, barrier = argv
+    (what `mpirun -n cores` over independent trials does, run_experiment.py:327), pinned to
+    one core.  Runs blocks of `steps` steps, every block started on a barrier; the number
+    of blocks is fixed by worker 0 after the first one so that they add up to min_seconds."""
+    wl, my_poses, warm, steps, use_ref, barrier, index, core, min_seconds, nblocks = argv
+    if core is not None:
+        try:
+            os.sched_setaffinity(0, {core})
+        except OSError:
+            pass
     L, tpath, _, kw = build_world_inputs(wl)
     agents = []
     if use_ref:
@@ -415,40 +422,64 @@ def _cpu_worker(argv):
     for _ in range(warm):
         for i in range(len(agents)):
             step(i)
-    barrier.wait()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        for i in range(len(agents)):
-            step(i)
-    return time.perf_counter() - t0, len(agents) * steps
+    times = []
+    while True:
+        barrier.wait()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for i in range(len(agents)):
+                step(i)
+        times.append(time.perf_counter() - t0)
+        if len(times) == 1:
+            if index == 0:
+                nblocks.value = int(max(1, min(500, np.ceil(min_seconds / max(times[0], 1e-6)))))
+            barrier.wait()
+        if len(times) >= nblocks.value:
+            break
+    return times, len(agents) * steps
 
 
-def cpu_run(wl, agents_per_core, warm, steps, cores, prefer_ref=True):
+def host_cores():
+    try:
+        return sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return list(range(os.cpu_count() or 1))
+
+
+def cpu_run(wl, agents_per_core, warm, steps, cores, prefer_ref=True, min_seconds=0.0):
+    """Returns (seconds of the median block, agent-steps per block, views, reference?, blocks)."""
     import multiprocessing as mp
     from oracle import ref_loader
     use_ref = prefer_ref and ref_loader.available()
+    if use_ref:
+        # loaded in THIS process too (the workers are forks of it): the compiled reference is
+        # then visible as a loaded library of the benchmark process itself
+        ref_loader.load_reference()
     L, tpath, poses, kw = build_world_inputs(wl)
     ctx = mp.get_context("fork")
-    barrier = ctx.Manager().Barrier(cores)
+    mgr = ctx.Manager()
+    barrier = mgr.Barrier(cores)
+    nblocks = mgr.Value("i", 1)
     n = agents_per_core * cores
     sel = poses[np.linspace(0, len(poses) - 1, n).astype(int)]
-    jobs = [(wl, sel[c * agents_per_core:(c + 1) * agents_per_core], warm, steps, use_ref, barrier)
-            for c in range(cores)]
+    ids = host_cores()
+    jobs = [(wl, sel[c * agents_per_core:(c + 1) * agents_per_core], warm, steps, use_ref, barrier, c,
+             ids[c] if len(ids) >= cores else None, min_seconds, nblocks) for c in range(cores)]
     with ctx.Pool(cores) as pool:
         res = pool.map(_cpu_worker, jobs)
-    t = max(r[0] for r in res)
+    blocks = np.max(np.array([r[0] for r in res]), axis=0)      # per block: the slowest worker
     agent_steps = sum(r[1] for r in res)
-    return t, agent_steps, len(tpath), use_ref
+    return float(np.median(blocks)), agent_steps, len(tpath), use_ref, [float(b) for b in blocks]
 
 
 def cpu_baseline(wl, target_seconds=15.0, cores=None):
-    cores = cores or os.cpu_count() or 1
+    cores = cores or len(host_cores())
     apc = 2
     # calibrate on 1 agent/core x 4 steps, then size the sample to ~target_seconds of wall clock
-    t, n, N, use_ref = cpu_run(wl, 1, 1, 4, cores)
+    t, n, N, use_ref, _ = cpu_run(wl, 1, 1, 4, cores)
     per_agent_step = t / 4
     steps = int(max(8, min(4000, target_seconds / max(per_agent_step * apc, 1e-6))))
-    t, n, N, use_ref = cpu_run(wl, apc, 2, steps, cores)
+    t, n, N, use_ref, _ = cpu_run(wl, apc, 2, steps, cores)
     A = wl["n_test_angles"]
     return {"value": n * A * N / t, "unit": UNIT, "cores": cores,
             "kind": "reference" if use_ref else "port",
@@ -464,10 +495,12 @@ def run_reference(args):
     if rank != 0:
         return
     wl = WORKLOAD
-    cores = args.cores or os.cpu_count() or 1
+    cores = args.cores or len(host_cores())
     K, W = args.steps, max(args.warmup, 1)
     apc = 1
-    t, n, N, use_ref = cpu_run(wl, apc, W, K, cores)
+    # blocks of K steps (every worker pinned to its own core, each block started on a barrier)
+    # repeated until they add up to >= 2 s; the record is the MEDIAN block
+    t, n, N, use_ref, blocks = cpu_run(wl, apc, W, K, cores, min_seconds=2.0)
     A = wl["n_test_angles"]
     value = n * A * N / t
     P = wl["sensor"][0] * wl["sensor"][1]
@@ -483,7 +516,9 @@ def run_reference(args):
         "agent_steps_per_sec": n / t,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores,
                          "kind": "reference" if use_ref else "port",
-                         "sample": "%d agents (one process per core) x %d steps" % (apc * cores, K)},
+                         "sample": "%d agents (one pinned process per core) x %d steps, median of %d such blocks "
+                                   "(%.2f s in all; fastest / slowest block %.3f / %.3f s)"
+                                   % (apc * cores, K, len(blocks), sum(blocks), min(blocks), max(blocks))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))

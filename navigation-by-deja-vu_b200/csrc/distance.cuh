@@ -32,6 +32,7 @@ struct DistArgs {
     const int *spans;             // [gridDim.x + 1] unit boundaries per CTA (k2_sad_v)
     int *step_counter;            // resident loop: device step index, bumped once per launch; else nullptr
     int *tie_count;               // resident loop: [0] tie work list length, [1] units done; reset per launch
+    unsigned long long *epoch;    // view shards over NVLink: launches so far (sequence base of the exchanges), else nullptr
     long long view_offset;        // global index of local view 0 (library shards)
     unsigned long long *keys;     // [G], pre-set to ~0
     double cw;
@@ -154,6 +155,7 @@ k2_sad_v(DistArgs a)
         *a.step_counter += 1;
         a.tie_count[0] = 0;   // list length
         a.tie_count[1] = 0;   // tie units completed (tie pass folded into move+sample)
+        if (a.epoch != nullptr) *a.epoch += 1;
     }
     if (total <= 0) return;
 
@@ -364,6 +366,7 @@ k2_sad_hsv(DistArgs a)
         *a.step_counter += 1;
         a.tie_count[0] = 0;   // list length
         a.tie_count[1] = 0;   // tie units completed (tie pass folded into move+sample)
+        if (a.epoch != nullptr) *a.epoch += 1;
     }
     const int words = a.Ppad / 4;
     uint32_t *sm = reinterpret_cast<uint32_t *>(smem);

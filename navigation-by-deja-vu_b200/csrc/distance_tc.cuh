@@ -51,6 +51,7 @@ struct TcArgs {
     int sad_const;               // C = P * sum of plane weights
     int *step_counter;           // resident loop: bumped once per launch, else nullptr
     int *tie_count;
+    unsigned long long *epoch;   // view shards over NVLink: launches so far (step.cuh), else nullptr
     int pdl_early;
     long long *tl;
 };
@@ -227,6 +228,7 @@ k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensor
         *a.step_counter += 1;
         a.tie_count[0] = 0;
         a.tie_count[1] = 0;
+        if (a.epoch != nullptr) *a.epoch += 1;
     }
 
     if (warp == 0) {

@@ -110,7 +110,7 @@ struct nvb_engine {
     int *d_spans_tc = nullptr;
     int span_tc_key[3] = {-1, -1, -1};
     // view-sharded library over NVLink peer memory
-    P2PArea *d_xarea = nullptr;
+    unsigned long long *d_xarea = nullptr;
     P2PArgs p2p{};
     bool p2p_on = false;
     unsigned long long *d_p2p_seq = nullptr;
@@ -800,6 +800,7 @@ static int launch_distance_tc(nvb_engine *e, int G, bool bump_step, bool encode_
     ta.sad_const = e->tc_sad_const;
     ta.step_counter = bump_step ? e->d_step : nullptr;
     ta.tie_count = bump_step ? e->d_tie_count : nullptr;
+    ta.epoch = (bump_step && e->p2p_on) ? e->d_p2p_seq : nullptr;
     ta.pdl_early = (bump_step && early_trigger()) ? 1 : 0;
     ta.tl = bump_step ? e->d_tl : nullptr;
     if (e->tc_kch == 128) return launch_tc_cfg<128, 4>(e, ta);
@@ -824,6 +825,7 @@ static int launch_distance(nvb_engine *e, int G, bool bump_step = false, bool gl
     da.n_vt = 0; da.vt_per_split = 0; da.spans = nullptr;
     da.step_counter = bump_step ? e->d_step : nullptr;
     da.tie_count = bump_step ? e->d_tie_count : nullptr;
+    da.epoch = (bump_step && e->p2p_on) ? e->d_p2p_seq : nullptr;
     da.view_offset = e->view_offset;
     da.keys = e->d_keys;
     da.cw = e->cw;
@@ -1266,7 +1268,7 @@ extern "C" int nvb_agents_set(nvb_engine *e, const double *poses, const int32_t 
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
     int rc;
-    if (e->p2p_on && (long long)B * e->A > e->p2p.cap) {
+    if (e->p2p_on && (B != e->p2p.B || (long long)B * e->A > e->p2p.cap)) {
         // the exchange area exported to the peers is too small for this batch: the peers hold
         // mappings of the old area, so the exchange is switched off until a new export + attach
         e->p2p_on = false;
@@ -1352,6 +1354,9 @@ static StepArgs make_step_args(nvb_engine *e, int fake, int log_afam)
     s.pdl_early = early_trigger() ? 1 : 0;
     s.tl = e->d_tl;
     s.out_best = e->zc_best; s.out_poses = e->zc_pose; s.out_sfam = e->zc_fam;
+    s.p2p = e->p2p;
+    if (!e->p2p_on) s.p2p.world = 0;
+    s.p2p.B = e->B;
     {   // thr2 = the largest double whose (correctly rounded) square root is <= thr, so that
         // d2 <= thr2  <=>  sqrt(d2) <= thr  (NavBySceneFamiliarity.py:271-276)
         const double thr = e->cvf * e->step_size;
@@ -1500,21 +1505,9 @@ static int launch_k31(nvb_engine *e, const StepArgs &s)
     return launch_k31_t<false, 0, 0>(e, s, sa, smem);
 }
 
-static int p2p_exchange(nvb_engine *e, unsigned long long *values)
-{
-    if (!e->p2p_on) return NVB_OK;
-    if ((long long)e->B * e->A > e->p2p.cap)
-        return fail(NVB_E_INVALID, "exchange area holds %lld values but the batch has %lld: export and attach again",
-                    e->p2p.cap, (long long)e->B * e->A);
-    CK(launch_seq(k_p2p_min, dim3(1), dim3(NVB_P2P_THREADS), 0, e->stream, e->p2p, values, e->B * e->A));
-    e->launches++;
-    return NVB_OK;
-}
-
 static int phase2(nvb_engine *e, const StepArgs &s)
 {
-    int xrc = p2p_exchange(e, e->d_keys);          // keys: MIN over ranks before anybody decides
-    if (xrc) return xrc;
+    // (view shards over NVLink: decide's prologue MINs the keys over the ranks, nvb_p2p_min_agent)
     k3_decide<<<e->B, NVB_STEP_THREADS, 0, e->stream>>>(s);
     k3_ties<<<e->sm_count * 4, NVB_TIE_THREADS, 0, e->stream>>>(s);
     e->launches += 2;
@@ -1524,8 +1517,7 @@ static int phase2(nvb_engine *e, const StepArgs &s)
 
 static int phase3(nvb_engine *e, const StepArgs &s)
 {
-    int xrc = p2p_exchange(e, e->d_exact);         // exact differences: MIN over ranks before the move
-    if (xrc) return xrc;
+    // (view shards over NVLink: the move's prologue MINs the exact differences over the ranks)
     if (e->n_path > NVB_PATH_SPLIT && !s.fake) {
         // long training path: pose update | grid-wide distance scan | bookkeeping
         const int chunks = (e->n_path + NVB_PATH_CHUNK - 1) / NVB_PATH_CHUNK;
@@ -1669,7 +1661,7 @@ static int run_steps(nvb_engine *e, int nsteps, int fake, int log_afam, bool eag
         // (+2 for the long-path move, +2 for the NVLink exchanges)
         const int ef = effective_form(e);
         const int per_step = fused_step(e) ? (ef == 3 ? 4 : (ef == 2 || ef == 4) ? 3 : 2)
-                                           : 5 + (e->n_path > NVB_PATH_SPLIT && !fake ? 2 : 0) + (e->p2p_on ? 2 : 0);
+                                           : 5 + (e->n_path > NVB_PATH_SPLIT && !fake ? 2 : 0) ;
         for (int i = done; i < nsteps; i++) {
             CK(cudaGraphLaunch(e->graph_exec, e->stream));
             e->launches += per_step;
@@ -2018,21 +2010,23 @@ extern "C" int nvb_p2p_export(nvb_engine *e, void *handle64)
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
     const long long cap = (long long)e->B * e->A;
-    const size_t bytes = sizeof(P2PArea) + sizeof(unsigned long long) * (size_t)(2 * cap);
+    // flags [2][ranks][B] + data [2][ranks][cap], sized for the largest world (step.cuh)
+    const size_t words = (size_t)2 * NVB_P2P_MAX_RANKS * ((size_t)e->B + (size_t)cap);
     e->p2p_on = false;
     e->graph_dirty = true;
     for (int i = 0; i < NVB_P2P_MAX_RANKS; i++)
         if (e->p2p_opened[i]) { cudaIpcCloseMemHandle(e->p2p_opened[i]); e->p2p_opened[i] = nullptr; }
     free_dev(e->d_xarea);
     e->d_xarea = nullptr;
-    CK(cudaMalloc((void **)&e->d_xarea, bytes));
-    CK(cudaMemset(e->d_xarea, 0, bytes));
+    CK(cudaMalloc((void **)&e->d_xarea, words * sizeof(unsigned long long)));
+    CK(cudaMemset(e->d_xarea, 0, words * sizeof(unsigned long long)));
     int rc;
     if ((rc = alloc_dev(&e->d_p2p_seq, 1))) return rc;
     if ((rc = alloc_dev(&e->d_p2p_err, 1))) return rc;
     CK(cudaMemset(e->d_p2p_seq, 0, sizeof(unsigned long long)));
     CK(cudaMemset(e->d_p2p_err, 0, sizeof(int)));
     e->p2p.cap = cap;
+    e->p2p.B = e->B;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, e->d_xarea));
     return NVB_OK;
@@ -2047,9 +2041,10 @@ extern "C" int nvb_p2p_attach(nvb_engine *e, int rank, int world, const void *ha
     e->p2p.self = e->d_xarea;
     e->p2p.rank = rank;
     e->p2p.world = world;
-    e->p2p.seq = e->d_p2p_seq;
+    e->p2p.epoch = e->d_p2p_seq;
     e->p2p.error = e->d_p2p_err;
     e->p2p.spin_limit = 4000000000ll;   // ~2 s of SM clock: a peer that never shows up is an error, not a hang
+    if (getenv("NAVSIM_B200_P2P_SPIN")) e->p2p.spin_limit = atoll(getenv("NAVSIM_B200_P2P_SPIN"));
     for (int p = 0; p < world; p++) {
         if (p == rank) { e->p2p.peer[p] = e->d_xarea; continue; }
         void *ptr = nullptr;
@@ -2057,7 +2052,7 @@ extern "C" int nvb_p2p_attach(nvb_engine *e, int rank, int world, const void *ha
         memcpy(&h, (const char *)handles64 + 64 * p, 64);
         CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
         e->p2p_opened[p] = ptr;
-        e->p2p.peer[p] = (P2PArea *)ptr;
+        e->p2p.peer[p] = (unsigned long long *)ptr;
     }
     e->p2p_on = true;
     e->graph_dirty = true;

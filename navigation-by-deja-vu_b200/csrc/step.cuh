@@ -34,6 +34,83 @@ struct AgentState {
     int32_t *stepped;       // [B] scratch: 1 if the agent takes part in the current step
 };
 
+// ---- MIN exchange over NVLink peer memory (view-sharded library, one process per GPU) ----
+// Every rank owns an exchange area that its peers have mapped through CUDA IPC:
+//   flags[2][world][B]      sequence number of the last push of (kind, source rank, agent)
+//   data [2][world][cap]    the pushed values, cap >= B * A
+// kind 0 = packed keys (exchanged in the prologue of decide), kind 1 = exact differences (in
+// the prologue of the move).  The exchange is PUSH based and per agent: the CTA of agent b
+// stores its A values and then a flag into EVERY PEER's area (P2P stores over NVLink), polls
+// its OWN area until the same agent's flags of all peers have arrived (local loads, bounded
+// spin: a missing peer becomes an error flag, not a hang) and takes the minimum of the values
+// that were pushed to it -- one NVLink store latency per exchange, no separate launch, no
+// round trip.  One buffer per kind suffices: a rank pushes the keys of step t+1 only after its
+// move of step t, which waited for every peer's exact differences of step t, which a peer
+// pushes after its decide of step t has finished reading the keys of step t (and likewise for
+// the other kind).  The sequence number is 2 * epoch + kind + 1 with a device-resident epoch
+// that the distance kernel bumps on every launch and nothing ever resets, so a whole run of
+// sharded steps replays as a CUDA graph without host round trips.
+// All ranks must queue the same sequence of step calls (they hold identical agent states).
+#define NVB_P2P_MAX_RANKS 8
+
+struct P2PArgs {
+    unsigned long long *self;                       // this rank's area
+    unsigned long long *peer[NVB_P2P_MAX_RANKS];    // every rank's area as mapped here (peer[rank] == self)
+    int rank, world, B;
+    long long cap;
+    const unsigned long long *epoch;                // device: distance-kernel launches so far
+    int *error;                                     // device: set to 1 if a peer did not show up in time
+    long long spin_limit;                           // clock64 ticks
+};
+
+__device__ __forceinline__ unsigned long long *nvb_p2p_flags(const P2PArgs &x, unsigned long long *area, int kind, int src)
+{
+    return area + ((size_t)kind * x.world + src) * x.B;
+}
+__device__ __forceinline__ unsigned long long *nvb_p2p_data(const P2PArgs &x, unsigned long long *area, int kind, int src)
+{
+    return area + (size_t)2 * x.world * x.B + ((size_t)kind * x.world + src) * x.cap;
+}
+
+// values[b * A .. b * A + A) := MIN over ranks, for the agent of this CTA.  Called by every
+// thread of the CTA; values are this rank's global buffer (keys or exact).  world <= 1: no-op.
+__device__ __forceinline__ void nvb_p2p_min_agent(const P2PArgs &x, unsigned long long *values, int b, int A, int kind)
+{
+    if (x.world <= 1) return;
+    const int tid = threadIdx.x;
+    const unsigned long long seq = 2ull * (*x.epoch) + (unsigned long long)kind + 1ull;
+    // push: my values of this agent into every peer's area, then (after a system-wide fence,
+    // by one thread per peer) the flag
+    for (int k = tid; k < A; k += blockDim.x) {
+        const unsigned long long v = values[(size_t)b * A + k];
+        for (int p = 0; p < x.world; p++)
+            if (p != x.rank) nvb_p2p_data(x, x.peer[p], kind, x.rank)[(size_t)b * A + k] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < x.world && tid != x.rank) {
+        *(volatile unsigned long long *)(nvb_p2p_flags(x, x.peer[tid], kind, x.rank) + b) = seq;
+        // wait for the same agent's push of peer `tid` to land in MY area
+        volatile unsigned long long *mine = nvb_p2p_flags(x, x.self, kind, tid) + b;
+        const long long t0 = clock64();
+        while (*mine < seq) {
+            if (clock64() - t0 > x.spin_limit) { *x.error = 1; break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    for (int k = tid; k < A; k += blockDim.x) {
+        unsigned long long m = values[(size_t)b * A + k];
+        for (int p = 0; p < x.world; p++) {
+            if (p == x.rank) continue;
+            const unsigned long long v = __ldcv(nvb_p2p_data(x, x.self, kind, p) + (size_t)b * A + k);
+            m = v < m ? v : m;
+        }
+        values[(size_t)b * A + k] = m;
+    }
+    __syncthreads();
+}
+
 struct StepArgs {
     AgentState ag;
     int B, A, N, P, Ppad;
@@ -77,6 +154,7 @@ struct StepArgs {
     double *out_poses;           // [B][3]
     double *out_sfam;            // [B]
     double cover_thr2;           // largest double whose sqrt is <= coverage_factor * step_size (host)
+    P2PArgs p2p;                 // exchange descriptor (view shards over NVLink); world == 0: none
 };
 
 #define NVB_PATH_BLOCK 16      /* path points per bounding circle (update_error prefilter) */
@@ -995,7 +1073,11 @@ k3_decide(StepArgs a)
     }
     __syncthreads();   // s_active, s_div
     const bool active = s_active != 0;
+    // view shards: the keys of this agent become the MIN over ranks before anything reads them.
+    // Every rank holds the same agent states, so `active` is the same everywhere and the
+    // exchange is skipped (by all of them) for an agent that takes no part in the step.
     if (!active) return;
+    nvb_p2p_min_agent(a.p2p, a.keys, b, a.A, 0);
     nvb_decide<false>(a, b, nullptr, s_div);
     nvb_tl_stamp(a.tl, 1, 2);
 }
@@ -1045,6 +1127,7 @@ k3_move(StepArgs a)
         nvb_log_idle(a, b);
         return;
     }
+    nvb_p2p_min_agent(a.p2p, a.exact, b, a.A, 1);   // view shards: exact differences, MIN over ranks
     double pose[3];
     const MovePre pre = nvb_move_preload(a, b, nullptr);
     nvb_move<0>(a, b, nullptr, pre, a.offsets, pose);
@@ -1065,6 +1148,7 @@ k3_move_pose(StepArgs a)
         nvb_log_idle(a, b);
         return;
     }
+    nvb_p2p_min_agent(a.p2p, a.exact, b, a.A, 1);   // view shards: exact differences, MIN over ranks
     double pose[3];
     const MovePre pre = nvb_move_preload(a, b, nullptr);
     nvb_move<1>(a, b, nullptr, pre, a.offsets, pose);
@@ -1109,67 +1193,3 @@ k3_move_finish(StepArgs a)
     nvb_move<2>(a, b, nullptr, pre, a.offsets, pose);
 }
 
-// ---- MIN exchange over NVLink peer memory (view-sharded library, one process per GPU) ----
-// Every rank owns an exchange area {flags[NVB_P2P_MAX_RANKS], data[2][cap]} that its peers
-// have mapped through CUDA IPC.  One exchange = publish my values (double buffered by the
-// exchange's parity), raise my flag in every peer's area (P2P store), wait until every
-// peer's flag for this exchange has arrived in MY area (local polling, bounded), then MIN
-// the peers' values into mine (P2P loads that bypass L1).  A rank can be at most one
-// exchange ahead of a peer -- it cannot pass the wait of exchange s+1 before that peer has
-// finished reading exchange s and published s+1 -- so two buffers suffice.  The sequence
-// number lives on the device and is bumped by the kernel, so the launch is graph-replayable
-// and a whole run of sharded steps is queued without any host round trip.
-#define NVB_P2P_MAX_RANKS 8
-#define NVB_P2P_THREADS 1024
-
-struct P2PArea {
-    unsigned long long flags[NVB_P2P_MAX_RANKS];
-    unsigned long long pad[8];
-    unsigned long long data[1];   // [2][cap]
-};
-
-struct P2PArgs {
-    P2PArea *self;
-    P2PArea *peer[NVB_P2P_MAX_RANKS];
-    int rank, world;
-    long long cap;
-    unsigned long long *seq;      // device: number of exchanges completed
-    int *error;                   // device: set to 1 if a peer did not show up in time
-    long long spin_limit;         // clock64 ticks
-};
-
-__global__ void __launch_bounds__(NVB_P2P_THREADS)
-k_p2p_min(P2PArgs x, unsigned long long *values, int n)
-{
-    nvb_grid_dep_wait();
-    const int tid = threadIdx.x;
-    const unsigned long long s = *x.seq;
-    unsigned long long *mine = x.self->data + (s & 1ull) * x.cap;
-    for (int i = tid; i < n; i += NVB_P2P_THREADS) mine[i] = values[i];
-    __threadfence_system();
-    __syncthreads();
-    if (tid < x.world && tid != x.rank) {
-        // raise my flag in the peer's area, then wait for the peer's flag in mine
-        volatile unsigned long long *theirs = x.peer[tid]->flags + x.rank;
-        *theirs = s + 1ull;
-        volatile unsigned long long *ours = x.self->flags + tid;
-        const long long t0 = clock64();
-        while (*ours < s + 1ull) {
-            if (clock64() - t0 > x.spin_limit) { *x.error = 1; break; }
-            __nanosleep(100);
-        }
-        __threadfence_system();
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += NVB_P2P_THREADS) {
-        unsigned long long m = values[i];
-        for (int p = 0; p < x.world; p++) {
-            if (p == x.rank) continue;
-            const unsigned long long v = __ldcv(x.peer[p]->data + (s & 1ull) * x.cap + i);
-            m = v < m ? v : m;
-        }
-        values[i] = m;
-    }
-    __syncthreads();
-    if (tid == 0) *x.seq = s + 1ull;
-}

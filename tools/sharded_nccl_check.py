@@ -3,8 +3,14 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29513 tools/sharded_nccl_check.py
 
-Every rank holds a contiguous slice of the library; the two MIN all-reduces of
-navsim/sharded.py run over NCCL.  The result must equal the unsharded engine's."""
+Every rank holds a contiguous slice of the library.  Three exchanges are checked against
+the unsharded engine, bit for bit: the two MIN all-reduces of navsim/sharded.py over NCCL
+with the engine on torch's stream, the same with a DEFAULT-constructed engine (its own
+non-blocking stream: ShardedStepper orders the streams itself), and the device-resident
+exchange over NVLink peer memory (csrc/step.cuh, nvb_p2p_min_agent) replayed as a CUDA
+graph.  Last, one rank queues a step its peers do not: the exchange must time out into
+p2p_error() == 1 instead of hanging.  tests/test_gpu_multi.py runs this file when the box
+has at least two GPUs."""
 import os
 import sys
 import time
@@ -54,6 +60,17 @@ def main():
         print("rank %d %-8s views [%d, %d) of %d: NCCL all-reduce  %s  (%.1f us/step, host-driven phases)" %
               (rank, name, off, off + cnt, len(scenes), "identical to unsharded" if same else "MISMATCH",
                dt / frames * 1e6), flush=True)
+        # a default-constructed engine: its own non-blocking stream, NCCL on torch's stream
+        eng_d = NavEngine(L, device=local, **w)
+        eng_d.set_library_shard(scenes[off:off + cnt], off, len(scenes), tpath)
+        eng_d.set_agents(poses, frames)
+        ShardedStepper(eng_d).step(frames)
+        eng_d.sync()
+        got_d = eng_d.log(0, frames)
+        same_d = np.array_equal(got_d["best_idx"], want["best_idx"]) and np.array_equal(got_d["poses"], want["poses"])
+        ok = ok and same_d
+        print("rank %d %-8s NCCL all-reduce, engine on its own stream: %s" %
+              (rank, name, "identical to unsharded" if same_d else "MISMATCH"), flush=True)
         # the same shards, exchanged over NVLink peer memory inside the step sequence
         eng2 = NavEngine(L, device=local, stream=stream.cuda_stream, **w)
         eng2.set_library_shard(scenes[off:off + cnt], off, len(scenes), tpath)
@@ -75,6 +92,32 @@ def main():
         print("rank %d %-8s views [%d, %d) of %d: NVLink P2P exchange %s  (%.1f us/step, device-resident)" %
               (rank, name, off, off + cnt, len(scenes), "identical to unsharded" if same2 else "MISMATCH",
                dt2 / frames * 1e6), flush=True)
+    # a peer that does not show up: rank 0 queues one step more than the others
+    os.environ["NAVSIM_B200_P2P_SPIN"] = "200000000"      # ~0.1 s of SM clock instead of ~2 s
+    L, w, tpath, pose, _ = build_case("c1_small")
+    full = NavEngine(L, device=local, **w)
+    assert full.train_from_path(tpath) == (0, -1)
+    scenes = full.familiar_scenes
+    off, cnt = shard_bounds(len(scenes), world, rank)
+    eng3 = NavEngine(L, device=local, **w)
+    eng3.set_library_shard(scenes[off:off + cnt], off, len(scenes), tpath)
+    eng3.set_agents(np.asarray(pose)[None], 50)
+    eng3.p2p_attach(rank, world)
+    eng3.step(4)
+    eng3.sync()
+    err_before = eng3.p2p_error()
+    dist.barrier()
+    t0 = time.perf_counter()
+    if rank == 0:
+        eng3.step(1)
+        eng3.sync()
+    waited = time.perf_counter() - t0
+    err_after = eng3.p2p_error()
+    timeout_ok = err_before == 0 and (err_after == 1 if rank == 0 else err_after == 0) and waited < 30.0
+    ok = ok and timeout_ok
+    print("rank %d missing peer: error flag %d -> %d after %.2f s  %s" %
+          (rank, err_before, err_after, waited, "ok" if timeout_ok else "WRONG"), flush=True)
+    dist.barrier()
     flag = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
