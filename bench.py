@@ -370,10 +370,126 @@ def run_ours(args):
 
     if world == 1 and rank == 0 and not args.no_cpu and not args.quick:
         line["cpu_baseline"] = cpu_baseline(wl, target_seconds=args.cpu_seconds, cores=args.cores)
+    if world > 1 and not args.quick:
+        # the one configuration with a real exchange step (BASELINE configs[3]): a 10^6-view
+        # library sharded by view over the ranks, MIN exchange over NVLink peer memory
+        try:
+            eng.close()
+            del flush
+            torch.cuda.empty_cache()
+            line["view_sharded"] = view_sharded_record(rank, world, local, dist)
+        except Exception as e:   # the record says so; the headline above stands on its own
+            line["view_sharded"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if world > 1:
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- view shards
+C4 = dict(name="C4: 10^6-view library sharded by view, 10 headings, sensor 40x2@2x4 (P=80), landscape 2000^2",
+          side=2000, seed=4004, sigma=6.0, sensor=(40, 2, 2, 4), n_test_angles=10, n_sensor_levels=5,
+          step_size=10.0, views=1000000, filler_seed=4704)
+
+
+def c4_world(c4=C4, views=None):
+    """Landscape, world kwargs, the genuine training path and the whole library: the path's own
+    views first, then views drawn from the level alphabet; one path point per
+    view (the last genuine point repeated)."""
+    from navsim import NavEngine, synthetic
+    n_total = int(views or c4["views"])
+    L = synthetic.make_landscape(c4["seed"], c4["side"], "stitch", sigma=c4["sigma"])
+    s = c4["sensor"]
+    kw = dict(sensor_dimensions=s[:2], sensor_pixel_dimensions=s[2:], step_size=c4["step_size"],
+              n_test_angles=c4["n_test_angles"], n_sensor_levels=c4["n_sensor_levels"],
+              max_distance_to_training_path=450.0)
+    tpath = synthetic.training_path_for(L.shape, c4["step_size"], c4["n_test_angles"], 0.0)
+    return L, kw, tpath, n_total
+
+
+def c4_library(c4, genuine, n_total):
+    from navsim import _cabi
+    rng = np.random.default_rng(c4["filler_seed"])
+    levels = np.unique(np.concatenate([[0], _cabi.quant_lut(c4["n_sensor_levels"])])).astype(np.uint8)
+    scenes = np.zeros((n_total,) + genuine.shape[1:], np.uint8)
+    scenes[..., 2] = levels[rng.integers(0, len(levels), scenes.shape[:3], dtype=np.uint8)]
+    k = min(len(genuine), n_total)
+    scenes[:k] = genuine[:k]
+    return scenes
+
+
+def view_sharded_record(rank, world, local, dist, agents=(1, 64), steps=20, views=None):
+    """Every rank holds the landscape, all agents and a contiguous slice of the library; the
+    per-step MIN exchanges run inside the decide / move kernels over NVLink peer memory.  The
+    same rank also runs the WHOLE library unsharded: heading log and poses must be identical."""
+    import torch
+    from navsim import NavEngine, synthetic
+    from navsim.sharded import shard_bounds
+    c4 = C4
+    L, kw, tpath, n_total = c4_world(c4, views)
+    eng0 = NavEngine(L, device=local, **kw)
+    rc, bad = eng0.train_from_path(tpath)
+    assert rc == 0, (rc, bad)
+    scenes = c4_library(c4, eng0.familiar_scenes, n_total)
+    eng0.close()
+    path = np.vstack([tpath, np.repeat(tpath[-1:], n_total - len(tpath), axis=0)]) if n_total > len(tpath) else tpath[:n_total]
+    off, cnt = shard_bounds(n_total, world, rank)
+    A, P = c4["n_test_angles"], c4["sensor"][0] * c4["sensor"][1]
+    stream = torch.cuda.current_stream()
+    out = {"workload": c4["name"], "views": n_total, "views_per_gpu": cnt, "n_gpus": world, "steps": steps,
+           "exchange": "NVLink peer memory, pushed per agent inside k3_decide / k3_move (csrc/step.cuh)", "runs": []}
+    ok_all = True
+    for B in agents:
+        n = int(round(np.sqrt(B)))
+        poses = (synthetic.start_pose_grid(tpath, 80, n_lat=n, n_deg=B // n) if B > 1
+                 else np.array([synthetic.start_pose(tpath, (0.05, 3.0), 80)]))
+        full = NavEngine(L, device=local, stream=stream.cuda_stream, **kw)
+        full.set_library(scenes, path)
+        full.set_agents(poses, steps)
+        full.step(steps)
+        want = full.log(0, steps)
+        full.rewind()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        full.step(steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t_one = e0.elapsed_time(e1) * 1e-3
+        kern_one = full.distance_kernel
+        full.close()
+        eng = NavEngine(L, device=local, stream=stream.cuda_stream, **kw)
+        eng.set_library_shard(scenes[off:off + cnt], off, n_total, path)
+        eng.set_agents(poses, steps)
+        eng.p2p_attach(rank, world)
+        eng.step(3)                      # plain launches + graph capture
+        eng.sync()
+        eng.rewind()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        eng.step(steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        got = eng.log(0, steps)
+        same = (np.array_equal(got["best_idx"], want["best_idx"]) and np.array_equal(got["poses"], want["poses"])
+                and eng.p2p_error() == 0)
+        flag = torch.tensor([int(same)], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok_all = ok_all and bool(flag.item())
+        out["runs"].append({
+            "agents": int(B), "us_per_step": float(t.item()) / steps * 1e6,
+            "comparisons_per_sec": B * A * n_total * steps / float(t.item()),
+            "one_gpu_whole_library_us_per_step": t_one / steps * 1e6,
+            "one_gpu_comparisons_per_sec": B * A * n_total * steps / t_one,
+            "speedup_vs_one_gpu": t_one / float(t.item()),
+            "distance_kernel": eng.distance_kernel, "distance_kernel_one_gpu": kern_one,
+            "identical_to_unsharded": bool(flag.item()), "p2p_error": eng.p2p_error()})
+        eng.close()
+    out["identical_to_unsharded"] = ok_all
+    assert ok_all, "view-sharded run differs from the unsharded engine: %r" % (out["runs"],)
+    return out
 
 
 # --------------------------------------------------------------------------- CPU arm

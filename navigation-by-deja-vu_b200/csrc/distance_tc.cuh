@@ -44,6 +44,8 @@ struct TcPlanes {
 struct TcArgs {
     int G, N;                    // glimpses, views (local shard)
     int n_vt;                    // view tiles
+    int n_gt;                    // glimpse tiles
+    int vt_major;                // item u = vt * n_gt + gt (consecutive items share a view tile) instead of gt * n_vt + vt
     int kchunks;                 // K-chunks of KCH bytes per row
     const int *spans;            // [gridDim.x + 1] item boundaries per CTA
     unsigned long long *keys;    // [G], pre-set to NVB_KEY_NONE
@@ -186,6 +188,21 @@ struct TcCfg {
     static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles start on swizzle-pattern boundaries");
 };
 
+// Work item u -> (glimpse tile, view tile).  gt-major keeps a CTA on one glimpse tile; vt-major
+// makes consecutive items share the VIEW tile: with a library far larger than L2 and a few
+// glimpse tiles, every view tile then comes from HBM once and is reused from L2 by the other
+// glimpse tiles (10^6 views x 640 glimpses: 0.4 GB of operand traffic instead of 1.9 GB).
+__device__ __forceinline__ void nvb_tc_item(const TcArgs &a, int u, int &gt, int &vt)
+{
+    if (a.vt_major) { vt = u / a.n_gt; gt = u - vt * a.n_gt; }
+    else { gt = u / a.n_vt; vt = u - gt * a.n_vt; }
+}
+__device__ __forceinline__ void nvb_tc_next(const TcArgs &a, int &gt, int &vt)
+{
+    if (a.vt_major) { if (++gt == a.n_gt) { gt = 0; vt++; } }
+    else { if (++vt == a.n_vt) { vt = 0; gt++; } }
+}
+
 template <int KCH, int NT, int STAGES>
 __global__ void __launch_bounds__(NVB_TC_THREADS, 1)
 k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, TcArgs a)
@@ -235,7 +252,8 @@ k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensor
         // ---- TMA producer
         int s = 0;
         uint32_t ph = 0;
-        int gt = u0 / a.n_vt, vt = u0 - gt * a.n_vt;
+        int gt, vt;
+        nvb_tc_item(a, u0, gt, vt);
         for (int u = u0; u < u1; u++) {
             for (int kc = 0; kc < a.kchunks; kc++) {
                 if (lane == 0) {
@@ -248,7 +266,7 @@ k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensor
                 __syncwarp();
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
-            if (++vt == a.n_vt) { vt = 0; gt++; }
+            nvb_tc_next(a, gt, vt);
         }
     } else if (warp == 1) {
         // ---- MMA issuer
@@ -285,7 +303,8 @@ k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensor
         // ---- epilogue: warp w may touch TMEM lanes 32 * (w % 4) .. + 31
         const int ew = warp & 3;
         const int row = ew * 32 + lane;
-        int gt = u0 / a.n_vt, vt = u0 - gt * a.n_vt;
+        int gt, vt;
+        nvb_tc_item(a, u0, gt, vt);
         int it = 0;
         for (int u = u0; u < u1; u++, it++) {
             const int buf = it & 1;
@@ -311,7 +330,7 @@ k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensor
                 const unsigned long long v = (unsigned long long)(a.view_offset + (long long)vt * NT + col);
                 atomicMin(a.keys + g, (sad << 32) | v);
             }
-            if (++vt == a.n_vt) { vt = 0; gt++; }
+            nvb_tc_next(a, gt, vt);
         }
     }
     nvb_tc_fence_before();

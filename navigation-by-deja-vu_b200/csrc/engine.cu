@@ -773,6 +773,8 @@ static int launch_tc_cfg(nvb_engine *e, TcArgs ta)
         e->graph_dirty = true;
     }
     ta.n_vt = n_vt;
+    ta.n_gt = n_gt;
+    ta.vt_major = (n_gt > 1 && (long long)ta.N * e->tc_Kpad > (32ll << 20)) ? 1 : 0;   // library beyond L2 reach: reuse view tiles
     ta.kchunks = e->tc_Kpad / KCH;
     ta.spans = e->d_spans_tc;
     CK(launch_seq(kern, dim3((unsigned)n_cta), dim3(NVB_TC_THREADS), (size_t)C::SMEM, e->stream, e->tm_genc, e->tm_lenc, ta));

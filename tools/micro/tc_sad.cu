@@ -106,7 +106,7 @@ static void run_tc(Ctx &c, const TcPlanes &pl, const uint8_t *d_level_of, const 
     CK(cudaMalloc(&d_spans, sizeof(int) * spans.size()));
     CK(cudaMemcpy(d_spans, spans.data(), sizeof(int) * spans.size(), cudaMemcpyHostToDevice));
     TcArgs a{};
-    a.G = c.G; a.N = c.N; a.n_vt = n_vt; a.kchunks = Kpad / KCH; a.spans = d_spans; a.keys = c.d_keys;
+    a.G = c.G; a.N = c.N; a.n_vt = n_vt; a.n_gt = n_gt; a.vt_major = getenv("TC_VT_MAJOR") ? 1 : 0; a.kchunks = Kpad / KCH; a.spans = d_spans; a.keys = c.d_keys;
     a.view_offset = 0; a.sad_const = 0;
     for (int k = 0; k < pl.n_planes; k++) a.sad_const += c.P * (int)pl.weight[k];
     cudaEvent_t e0, e1;
