@@ -159,7 +159,7 @@ def label_image(image):
     """skimage.measure.label for a 2-D image: 8-connected components of the non-zero pixels,
     numbered in raster order of their first pixel."""
     from scipy import ndimage
-    return ndimage.label(np.asarray(image) != 0, structure=np.ones((3, 3), int))[0]
+    return ndimage.label(np.asarray(image) != 0, structure=np.ones((3, 3), int))[0].astype(np.int64)   # skimage returns intp
 
 
 def region_props(labels):

@@ -45,10 +45,37 @@ class NavEngine(object):
         check(self._lib.nvb_engine_create(dev, C.c_void_p(int(stream)) if stream is not None else None,
                                           C.byref(self._h)))
         self.device = dev
+        self.landscape = None
+        self.set_landscape(landscape)
+        self.set_world(sensor_dimensions, step_size, n_test_angles=n_test_angles,
+                       sensor_pixel_dimensions=sensor_pixel_dimensions,
+                       max_distance_to_training_path=max_distance_to_training_path,
+                       n_sensor_levels=n_sensor_levels, mask_middle_n=mask_middle_n,
+                       threshold_factor=threshold_factor, coverage_threshold_factor=coverage_threshold_factor,
+                       saccade_degrees=saccade_degrees, chem_weight=chem_weight)
+
+    def set_landscape(self, landscape):
+        """Uploads another landscape (any strides: flipped views are fine).  The sensor stays;
+        library and agents must be set again."""
         landscape = np.asarray(landscape)
         if landscape.dtype != np.uint8 or landscape.ndim != 3 or landscape.shape[2] != 3:
             raise ValueError("landscape must be a (rows, cols, 3) uint8 HSV array")
         self.landscape = landscape
+        s = landscape.strides
+        check(self._lib.nvb_set_landscape(self._h, ptr(landscape), landscape.shape[0],
+                                          landscape.shape[1], s[0], s[1], s[2]))
+        self.training_path = None
+        self.n_views = 0
+        self.n_agents = 0
+        self._familiar_scenes = None
+
+    def set_world(self, sensor_dimensions, step_size, n_test_angles=60, sensor_pixel_dimensions=[1, 1],
+                  max_distance_to_training_path=np.inf, n_sensor_levels=5, mask_middle_n=0,
+                  threshold_factor=2., coverage_threshold_factor=0.8, saccade_degrees=180., chem_weight=0.0):
+        """(Re)configures sensor, heading sweep and navigation parameters on the landscape the
+        engine already holds -- what the reference's constructor does
+        (NavBySceneFamiliarity.py:59-116) without a new engine, stream or landscape upload:
+        a parameter sweep walks through its worlds on one engine per device."""
         self.sensor_dimensions = np.asarray(sensor_dimensions)
         self.sensor_pixel_dimensions = np.asarray(sensor_pixel_dimensions)
         footprint = self.sensor_dimensions * self.sensor_pixel_dimensions
@@ -74,10 +101,6 @@ class NavEngine(object):
         self.n_views = 0
         self.n_agents = 0
         self._familiar_scenes = None
-
-        s = landscape.strides
-        check(self._lib.nvb_set_landscape(self._h, ptr(landscape), landscape.shape[0],
-                                          landscape.shape[1], s[0], s[1], s[2]))
         lut = np.ascontiguousarray(np.stack([_cabi.quant_lut(n) for n in n_sensor_levels]))
         check(self._lib.nvb_set_sensor(self._h, int(self.sensor_dimensions[0]),
                                        int(self.sensor_dimensions[1]),
@@ -410,22 +433,36 @@ class NavEngine(object):
         return self._lib.nvb_device_ptr(self._h, int(which))
 
 
+def _window_all(coverage, k):
+    """w[i] = all(coverage[i:i + k]) for i in 0 .. n - k (an empty window is all-true)."""
+    c = np.asarray(coverage).astype(bool)
+    n = len(c)
+    if k <= 0:
+        return np.ones(n + 1, bool)
+    cs = np.concatenate([[0], np.cumsum(c, dtype=np.int64)])
+    return (cs[k:] - cs[:n - k + 1]) == k
+
+
 def percent_recapitulated_forgiving(coverage, n_consecutive_scenes=0.05):
-    """NavBySceneFamiliarity.py:218-232 on a coverage bitmap."""
+    """NavBySceneFamiliarity.py:218-232 on a coverage bitmap: the end i of the LAST window of
+    k consecutive covered scenes, as a fraction of the path (0 if there is none); the
+    reference's backwards loop with one cumulative sum."""
     n = len(coverage)
     k = int(n_consecutive_scenes * n)
-    for i in range(n, k - 1, -1):
-        if np.all(coverage[i - k:i]):
-            return i / n
-    return 0.
+    if n == 0:
+        return 0.
+    w = _window_all(coverage, k)          # window coverage[i - k:i] for i = k .. n  <->  w[i - k]
+    hits = np.nonzero(w)[0]
+    return (int(hits[-1]) + k) / n if len(hits) else 0.
 
 
 def n_captures(coverage, n_consecutive_scenes=0.05):
-    """NavBySceneFamiliarity.py:235-249 on a coverage bitmap."""
-    n = len(coverage)
+    """NavBySceneFamiliarity.py:235-249 on a coverage bitmap: positions i < n - k that are not
+    covered while the k scenes after them all are."""
+    c = np.asarray(coverage).astype(bool)
+    n = len(c)
     k = int(n_consecutive_scenes * n)
-    out = 0
-    for i in range(n - k):
-        if (not coverage[i]) and np.all(coverage[i + 1:i + 1 + k]):
-            out += 1
-    return out
+    if n - k <= 0:
+        return 0
+    w = _window_all(c, k)                 # w[j] = all(c[j:j + k])
+    return int(np.sum(~c[:n - k] & w[1:n - k + 1]))

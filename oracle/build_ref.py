@@ -5,6 +5,13 @@ TEST INFRASTRUCTURE ONLY.  Compiles, from the sources where they lie under
 
   navsim/util.pyx                  -> oracle/_ref/navsim/util.<abi>.so
   navsim/NavBySceneFamiliarity.py  -> oracle/_ref/navsim/NavBySceneFamiliarity.<abi>.so
+  scripts/run_experiment.py        -> oracle/_ref/scripts/run_experiment.<abi>.so    (byte-identical)
+  scripts/load_experiments.py      -> oracle/_ref/scripts/load_experiments.<abi>.so  (byte-identical)
+
+The two driver scripts are compiled so that the reference's UNMODIFIED entry points can be
+executed on the GPU box (where /root/reference does not exist) on top of the product package:
+tests/test_gpu_reference_driver.py loads run_experiment's module body as __main__ through
+navsim.run_reference.
 
 No reference source enters the repository: the two files are copied to a
 scratch directory under /tmp, built there, and only the shared objects are
@@ -27,12 +34,14 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = os.environ.get("NAVSIM_REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref", "navsim")
+OUT_SCRIPTS = os.path.join(HERE, "_ref", "scripts")
 
 _SETUP = """
 from setuptools import setup
 from Cython.Build import cythonize
 import numpy as np
-setup(ext_modules=cythonize(["navsim/util.pyx", "navsim/NavBySceneFamiliarity.py"],
+setup(ext_modules=cythonize(["navsim/util.pyx", "navsim/NavBySceneFamiliarity.py",
+                             "scripts/run_experiment.py", "scripts/load_experiments.py"],
                             language_level=3),
       include_dirs=[np.get_include()], script_args=["build_ext", "--inplace"])
 """
@@ -40,7 +49,9 @@ setup(ext_modules=cythonize(["navsim/util.pyx", "navsim/NavBySceneFamiliarity.py
 
 def have_ref():
     return (len(glob.glob(os.path.join(OUT, "util.*.so"))) > 0
-            and len(glob.glob(os.path.join(OUT, "NavBySceneFamiliarity.*.so"))) > 0)
+            and len(glob.glob(os.path.join(OUT, "NavBySceneFamiliarity.*.so"))) > 0
+            and len(glob.glob(os.path.join(OUT_SCRIPTS, "run_experiment.*.so"))) > 0
+            and len(glob.glob(os.path.join(OUT_SCRIPTS, "load_experiments.*.so"))) > 0)
 
 
 def build(force=False):
@@ -60,6 +71,10 @@ def build(force=False):
             f.write(pyx.replace("np.int_t", "long"))
         shutil.copy(os.path.join(src, "NavBySceneFamiliarity.py"), pkg)
         open(os.path.join(pkg, "__init__.py"), "w").close()
+        scr = os.path.join(tmp, "scripts")
+        os.makedirs(scr)
+        for name in ("run_experiment.py", "load_experiments.py"):
+            shutil.copy(os.path.join(REF_ROOT, "scripts", name), scr)
         with open(os.path.join(tmp, "setup_ref.py"), "w") as f:
             f.write(_SETUP)
         subprocess.check_call([sys.executable, "setup_ref.py"], cwd=tmp,
@@ -67,6 +82,10 @@ def build(force=False):
         os.makedirs(OUT, exist_ok=True)
         for so in glob.glob(os.path.join(pkg, "*.so")):
             shutil.copy(so, OUT)
+        os.makedirs(OUT_SCRIPTS, exist_ok=True)
+        # (scripts/ is no package: build_ext --inplace leaves these two next to setup_ref.py)
+        for so in glob.glob(os.path.join(scr, "*.so")) + glob.glob(os.path.join(tmp, "*.so")):
+            shutil.copy(so, OUT_SCRIPTS)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     return have_ref()
