@@ -53,6 +53,8 @@ struct TcArgs {
     int sad_const;               // C = P * sum of plane weights
     int *step_counter;           // resident loop: bumped once per launch, else nullptr
     int *tie_count;
+    int2 *cand;                  // TOP2 kernels: [G][n_vt] the two smallest tile-local keys (-256 * dot + column) per
+                                 // glimpse and view tile (0x7FFFFFFF = none), for the candidate-based decide
     unsigned long long *epoch;   // view shards over NVLink: launches so far (step.cuh), else nullptr
     int pdl_early;
     long long *tl;
@@ -176,6 +178,36 @@ __device__ __forceinline__ int nvb_tc_fold(uint32_t taddr, int c0, int nvalid, i
     return best;
 }
 
+// The same keeping the TWO smallest keys of the row (best <= second): the step kernel that
+// follows resolves headings tied at the integer minimum from these candidates instead of
+// rescanning the library (step.cuh, nvb_decide_cand).  Second smallest of {best, second, lo, hi}
+// with best <= second, lo <= hi is min3(max(best, lo), second, hi).
+template <int W>
+__device__ __forceinline__ void nvb_tc_fold2(uint32_t taddr, int c0, int nvalid, int &best, int &second)
+{
+    uint32_t r[W];
+    if (W == 32) nvb_tmem_ld32(taddr + (uint32_t)c0, reinterpret_cast<uint32_t (&)[32]>(r));
+    else nvb_tmem_ld16(taddr + (uint32_t)c0, reinterpret_cast<uint32_t (&)[16]>(r));
+    nvb_tmem_wait_ld();
+    if (c0 + W <= nvalid) {
+#pragma unroll
+        for (int j = 0; j + 1 < W; j += 2) {
+            const int k1 = (int)r[j] * -256 + (c0 + j), k2 = (int)r[j + 1] * -256 + (c0 + j + 1);
+            const int lo = min(k1, k2), hi = max(k1, k2);
+            second = __vimin3_s32(max(best, lo), second, hi);
+            best = min(best, lo);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; j++)
+            if (c0 + j < nvalid) {
+                const int k1 = (int)r[j] * -256 + (c0 + j);
+                second = min(second, max(best, k1));
+                best = min(best, k1);
+            }
+    }
+}
+
 template <int KCH, int NT, int STAGES>
 struct TcCfg {
     static constexpr int TM = NVB_TC_TM;
@@ -203,7 +235,7 @@ __device__ __forceinline__ void nvb_tc_next(const TcArgs &a, int &gt, int &vt)
     else { if (++vt == a.n_vt) { vt = 0; gt++; } }
 }
 
-template <int KCH, int NT, int STAGES>
+template <int KCH, int NT, int STAGES, bool TOP2 = false>
 __global__ void __launch_bounds__(NVB_TC_THREADS, 1)
 k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, TcArgs a)
 {
@@ -314,15 +346,22 @@ k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensor
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256);
             const int nvalid = min(NT, a.N - vt * NT);
             int best = 0x7FFFFFFF;   // min over columns of -256 * dot + column
+            int second = 0x7FFFFFFF;
 #pragma unroll
             for (int c0 = 0; c0 < NT; c0 += 32) {
-                if (NT - c0 >= 32) best = nvb_tc_fold<32>(taddr, c0, nvalid, best);
-                else best = nvb_tc_fold<16>(taddr, c0, nvalid, best);
+                if (TOP2) {
+                    if (NT - c0 >= 32) nvb_tc_fold2<32>(taddr, c0, nvalid, best, second);
+                    else nvb_tc_fold2<16>(taddr, c0, nvalid, best, second);
+                } else {
+                    if (NT - c0 >= 32) best = nvb_tc_fold<32>(taddr, c0, nvalid, best);
+                    else best = nvb_tc_fold<16>(taddr, c0, nvalid, best);
+                }
             }
             nvb_tc_fence_before();
             __syncwarp();
             if (lane == 0) nvb_mbar_arrive(tempty + buf);
             const int g = gt * C::TM + row;
+            if (TOP2 && g < a.G) a.cand[(size_t)g * a.n_vt + vt] = make_int2(best, second);
             if (g < a.G && best != 0x7FFFFFFF) {
                 const int col = best & 255;
                 const int dot = -(best >> 8);

@@ -109,6 +109,8 @@ struct nvb_engine {
     CUtensorMap tm_genc, tm_lenc;
     int *d_spans_tc = nullptr;
     int span_tc_key[3] = {-1, -1, -1};
+    int2 *d_cand = nullptr;         // [Gcap][n_vt] two best candidates per glimpse and view tile (TOP2 kernel)
+    long long cand_cap = 0;
     // view-sharded library over NVLink peer memory
     unsigned long long *d_xarea = nullptr;
     P2PArgs p2p{};
@@ -288,11 +290,25 @@ static PFN_tmapEncodeTiled tmap_encoder()
 // ---- tensor-core distance kernel: operand planes, buffers, tensor maps ---------------------
 // NAVSIM_B200_NO_TC=1 keeps every configuration on the byte-SIMD kernel (k2_sad_v).
 #define NVB_TC_MIN_G 96   /* fewer glimpses than this leave most of a 128-row MMA tile empty */
+#define NVB_TC_NT 256     /* views per MMA tile (UMMA N) */
 
 static bool use_tc(const nvb_engine *e, long long G)
 {
     static const bool off = getenv("NAVSIM_B200_NO_TC") != nullptr;
     return e->tc_ok && !e->tc_off && e->cw == 0.0 && G >= NVB_TC_MIN_G && !off;
+}
+
+// The step after the tensor-core distance kernel as ONE launch (decide from the kernel's two
+// best candidates per view tile + move + sample, step.cuh k3_move_sample<.., CAND>) instead of
+// decide | grid-wide tie pass | move + sample: small un-sharded libraries whose batch the
+// tensor-core kernel scores, sweeps of up to 512 headings, at most 64 view tiles.
+// NAVSIM_B200_NO_CAND=1 keeps the three-launch form.
+static bool fused_step(const nvb_engine *e);
+static bool cand_form(const nvb_engine *e)
+{
+    static const bool off = getenv("NAVSIM_B200_NO_CAND") != nullptr;
+    return !off && fused_step(e) && use_tc(e, (long long)e->B * e->A) && e->lenc_valid && e->tc_lib_ok &&
+           e->A <= NVB_STEP_MAX_A_SMEM && (e->N + NVB_TC_NT - 1) / NVB_TC_NT <= 64 && step_form() == 3;
 }
 
 // Thermometer planes of the V-channel quantisation table (distance_tc.cuh): levels = the
@@ -364,7 +380,6 @@ static int make_tc_map(CUtensorMap *m, void *base, long long rows, int Kpad, int
     return NVB_OK;
 }
 
-#define NVB_TC_NT 256   /* views per MMA tile (UMMA N) */
 
 // Encoded glimpse buffer for Gcap glimpses (zeroed: the K padding must be 0) + its tensor map.
 static int ensure_tc_glimpses(nvb_engine *e, long long Gcap)
@@ -484,7 +499,7 @@ extern "C" void nvb_engine_destroy(nvb_engine *e)
                     e->ag.budget, e->ag.nav_frames, e->ag.err_sum, e->ag.err_n, e->ag.coverage,
                     e->ag.stepped, e->d_step, e->log_best, e->log_pose, e->log_sfam, e->log_afam,
                     e->d_poses0, e->d_budget0, e->d_spans, e->d_pending, e->d_dmin2, e->d_pblk,
-                    e->d_tc_tab, e->d_tc_level_of, e->d_genc, e->d_lenc, e->d_spans_tc, e->d_tc_bad};
+                    e->d_tc_tab, e->d_tc_level_of, e->d_genc, e->d_lenc, e->d_spans_tc, e->d_tc_bad, e->d_cand};
     for (int i = 0; i < NVB_P2P_MAX_RANKS; i++)
         if (e->p2p_opened[i]) cudaIpcCloseMemHandle(e->p2p_opened[i]);
     free_dev(e->d_xarea); free_dev(e->d_p2p_seq); free_dev(e->d_p2p_err);
@@ -746,11 +761,11 @@ static int launch_dist_cpr(nvb_engine *e, const DistArgs &da)
     return launch_dist_cfg<16, 4, 16, CPR>(e, da);
 }
 
-template <int KCH, int STAGES>
+template <int KCH, int STAGES, bool TOP2>
 static int launch_tc_cfg(nvb_engine *e, TcArgs ta)
 {
     using C = TcCfg<KCH, NVB_TC_NT, STAGES>;
-    auto kern = k2_tc<KCH, NVB_TC_NT, STAGES>;
+    auto kern = k2_tc<KCH, NVB_TC_NT, STAGES, TOP2>;
     static bool attr_set[64] = {false};
     if (!attr_set[e->device & 63]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -805,8 +820,22 @@ static int launch_distance_tc(nvb_engine *e, int G, bool bump_step, bool encode_
     ta.epoch = (bump_step && e->p2p_on) ? e->d_p2p_seq : nullptr;
     ta.pdl_early = (bump_step && early_trigger()) ? 1 : 0;
     ta.tl = bump_step ? e->d_tl : nullptr;
-    if (e->tc_kch == 128) return launch_tc_cfg<128, 4>(e, ta);
-    return launch_tc_cfg<64, 8>(e, ta);
+    ta.cand = nullptr;
+    if (bump_step && cand_form(e)) {
+        // the candidate-based step: the two best views per glimpse and view tile (step.cuh)
+        const long long n_vt = (e->N + NVB_TC_NT - 1) / NVB_TC_NT, need = (long long)e->Gcap * n_vt;
+        if (need > e->cand_cap) {
+            int rc = alloc_dev(&e->d_cand, (size_t)need);
+            if (rc) return rc;
+            e->cand_cap = need;
+            e->graph_dirty = true;
+        }
+        ta.cand = e->d_cand;
+        if (e->tc_kch == 128) return launch_tc_cfg<128, 4, true>(e, ta);
+        return launch_tc_cfg<64, 8, true>(e, ta);
+    }
+    if (e->tc_kch == 128) return launch_tc_cfg<128, 4, false>(e, ta);
+    return launch_tc_cfg<64, 8, false>(e, ta);
 }
 
 // K2 over glimpses [0, G) of the engine's glimpse buffers; keys must be reset.
@@ -1356,6 +1385,9 @@ static StepArgs make_step_args(nvb_engine *e, int fake, int log_afam)
     s.pdl_early = early_trigger() ? 1 : 0;
     s.tl = e->d_tl;
     s.out_best = e->zc_best; s.out_poses = e->zc_pose; s.out_sfam = e->zc_fam;
+    s.cand = e->d_cand;
+    s.n_vt = (e->N + NVB_TC_NT - 1) / NVB_TC_NT;
+    s.sad_const = e->tc_sad_const;
     s.p2p = e->p2p;
     if (!e->p2p_on) s.p2p.world = 0;
     s.p2p.B = e->B;
@@ -1480,6 +1512,25 @@ static int launch_k3ms_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa
     return NVB_OK;
 }
 
+template <bool HS, int PH, int PW>
+static int launch_k3cand_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa, size_t smem)
+{
+    static size_t attr_set[64] = {0};
+    size_t &cur = attr_set[e->device & 63];
+    auto kern = k3_move_sample<HS, PH, PW, false, true>;
+    if (smem > cur) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    const long long items = (long long)e->A * e->P;
+    const long long w128 = ((items + 127) / 128) * 128, w160 = ((items + 159) / 160) * 160;
+    const int threads = w160 < w128 ? NVB_MS_MAX_THREADS : NVB_STEP_THREADS;
+    CK(launch_seq(kern, dim3(e->B), dim3(threads), smem, e->stream, e->tmap, s, sa));
+    e->launches += 1;
+    CK(cudaGetLastError());
+    return NVB_OK;
+}
+
 // [decide + cooperative tie scan] then [move + sample next]
 static int launch_k3_split(nvb_engine *e, const StepArgs &s)
 {
@@ -1487,6 +1538,12 @@ static int launch_k3_split(nvb_engine *e, const StepArgs &s)
     const int nplanes = sa.need_hs ? 3 : 1;
     const size_t smem = e->R > 0 ? nvb_sampler_smem(e->BW, e->BH, nplanes, sa.A)
                                  : nvb_sampler_smem(0, 0, 0, sa.A);
+    if (cand_form(e) && e->d_cand != nullptr) {   // (need_hs implies chem_weight > 0: never the tensor-core kernel)
+        if (e->ph == 4 && e->pw == 2) return launch_k3cand_t<false, 4, 2>(e, s, sa, smem);
+        if (e->ph == 2 && e->pw == 2) return launch_k3cand_t<false, 2, 2>(e, s, sa, smem);
+        if (e->ph == 1 && e->pw == 1) return launch_k3cand_t<false, 1, 1>(e, s, sa, smem);
+        return launch_k3cand_t<false, 0, 0>(e, s, sa, smem);
+    }
     if (sa.need_hs) return launch_k3ms_t<true, 0, 0>(e, s, sa, smem);
     if (e->ph == 4 && e->pw == 2) return launch_k3ms_t<false, 4, 2>(e, s, sa, smem);
     if (e->ph == 2 && e->pw == 2) return launch_k3ms_t<false, 2, 2>(e, s, sa, smem);
@@ -1662,7 +1719,7 @@ static int run_steps(nvb_engine *e, int nsteps, int fake, int log_afam, bool eag
         // launches per step-batch: K2, decide, ties, move+sample | K1, K2, decide, ties, move
         // (+2 for the long-path move, +2 for the NVLink exchanges)
         const int ef = effective_form(e);
-        const int per_step = fused_step(e) ? (ef == 3 ? 4 : (ef == 2 || ef == 4) ? 3 : 2)
+        const int per_step = fused_step(e) ? ((cand_form(e) && e->d_cand) ? 2 : ef == 3 ? 4 : (ef == 2 || ef == 4) ? 3 : 2)
                                            : 5 + (e->n_path > NVB_PATH_SPLIT && !fake ? 2 : 0) ;
         for (int i = done; i < nsteps; i++) {
             CK(cudaGraphLaunch(e->graph_exec, e->stream));

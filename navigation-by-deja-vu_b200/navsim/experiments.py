@@ -98,11 +98,19 @@ class LandscapeStore(object):
     <landscape_dir>/<class>/<name> the way make_nsf does: PIL -> HSV, grains = 8-connected
     components of (V >= 200) after a modal filter, memoised per (class, name)."""
 
-    def __init__(self, landscapes=None, landscape_dir=None, seed=None):
+    def __init__(self, landscapes=None, landscape_dir=None, seed=None, trials=None):
         self.arrays = dict(landscapes or {})
         self.dir = landscape_dir
         self.rng = np.random.default_rng(seed)     # the reference's RNG is unseeded (run_experiment.py:2)
         self._grains = {}
+        # make_nsf memoises (landscape, grain labels, grain properties) per (class, name) ONLY
+        # (run_experiment.py:163-182): the grains of a landscape are labelled with the
+        # min_chem_grain_diameter of the FIRST trial that uses it and reused by every later
+        # trial, whatever its own value.  Kept: the drop-in must give the reference's rows.
+        self.first_min_d = {}
+        for tr in (trials or []):
+            k = (tr.get('landscape_class', ''), tr['landscape_name'])
+            self.first_min_d.setdefault(k, tr.get('min_chem_grain_diameter', 2))
 
     def base(self, cls, name):
         if name in self.arrays:
@@ -115,7 +123,8 @@ class LandscapeStore(object):
         return self.arrays[key]
 
     def grains(self, cls, name, min_diameter):
-        key = (cls, name, min_diameter)
+        min_diameter = self.first_min_d.get((cls, name), min_diameter)
+        key = (cls, name)
         if key not in self._grains:
             from . import compat
             land = self.base(cls, name)
@@ -201,7 +210,7 @@ def run_trials(trials, landscapes=None, device=None, landscape_dir=None, workers
     (key, indices) groups (a rank's share); results of the others stay None.
     workers > 1: that many host threads, each with its own engine and stream on `device`,
     take worlds from a shared queue (small worlds leave most of a B200 idle)."""
-    store = LandscapeStore(landscapes, landscape_dir, seed)
+    store = LandscapeStore(landscapes, landscape_dir, seed, trials)
     worlds = group_worlds(trials) if worlds is None else worlds
     results = [None] * len(trials)
     if workers <= 1:
