@@ -821,15 +821,9 @@ static int launch_distance_tc(nvb_engine *e, int G, bool bump_step, bool encode_
     ta.pdl_early = (bump_step && early_trigger()) ? 1 : 0;
     ta.tl = bump_step ? e->d_tl : nullptr;
     ta.cand = nullptr;
-    if (bump_step && cand_form(e)) {
-        // the candidate-based step: the two best views per glimpse and view tile (step.cuh)
-        const long long n_vt = (e->N + NVB_TC_NT - 1) / NVB_TC_NT, need = (long long)e->Gcap * n_vt;
-        if (need > e->cand_cap) {
-            int rc = alloc_dev(&e->d_cand, (size_t)need);
-            if (rc) return rc;
-            e->cand_cap = need;
-            e->graph_dirty = true;
-        }
+    if (bump_step && cand_form(e) && e->d_cand != nullptr) {
+        // the candidate-based step: the two best views per glimpse and view tile (step.cuh;
+        // the array is allocated by prepare_step_buffers before the step arguments are built)
         ta.cand = e->d_cand;
         if (e->tc_kch == 128) return launch_tc_cfg<128, 4, true>(e, ta);
         return launch_tc_cfg<64, 8, true>(e, ta);
@@ -1353,8 +1347,27 @@ extern "C" int nvb_agents_set(nvb_engine *e, const double *poses, const int32_t 
     return NVB_OK;
 }
 
+static int ensure_tc_library(nvb_engine *e);
+
+// Buffers the step kernels are handed by value must exist before the arguments are built:
+// the encoded library (decides whether the tensor-core kernel runs) and, for the
+// candidate-based step, the candidate array.
+static void prepare_step_buffers(nvb_engine *e)
+{
+    if (!use_tc(e, (long long)e->B * e->A) || e->N <= 0) return;
+    if (ensure_tc_library(e) != NVB_OK) return;
+    if (!cand_form(e)) return;
+    const long long n_vt = (e->N + NVB_TC_NT - 1) / NVB_TC_NT, need = (long long)e->Gcap * n_vt;
+    if (need > e->cand_cap) {
+        if (alloc_dev(&e->d_cand, (size_t)need) != NVB_OK) { e->d_cand = nullptr; e->cand_cap = 0; return; }
+        e->cand_cap = need;
+        e->graph_dirty = true;
+    }
+}
+
 static StepArgs make_step_args(nvb_engine *e, int fake, int log_afam)
 {
+    prepare_step_buffers(e);
     StepArgs s;
     s.ag = e->ag;
     s.B = e->B; s.A = e->A; s.N = e->N; s.P = e->P; s.Ppad = e->Ppad;

@@ -380,6 +380,38 @@ __device__ __forceinline__ void nvb_decide(const StepArgs &a, int b, unsigned lo
 // tile's first two both tie -- the rest of that tile, rescanned by the whole CTA.  No pass over
 // the library, no second launch.  Results: s_exact[k] (k < NVB_STEP_MAX_A_SMEM) / a.exact.
 #define NVB_CAND_JOBS 24
+// (not inlined, and handed plain pointers rather than the argument struct -- whose address
+// would force a copy of it into local memory: the candidate code sits in front of the
+// register-tight move+sample kernel.  V plane only: the tensor-core kernel implies chem_weight 0.)
+__device__ __noinline__ unsigned long long nvb_exact_bits(const uint8_t *qrow, const uint8_t *frow, int nc,
+                                                          const double *div255)
+{
+    const uint4 *q = reinterpret_cast<const uint4 *>(qrow);
+    const uint4 *f = reinterpret_cast<const uint4 *>(frow);
+    double diff = 0.0;
+    for (int c = 0; c < nc; c++) {
+        const uint4 qq = q[c], ff = __ldg(f + c);
+        const uint32_t d[4] = {__vabsdiffu4(qq.x, ff.x), __vabsdiffu4(qq.y, ff.y), __vabsdiffu4(qq.z, ff.z),
+                               __vabsdiffu4(qq.w, ff.w)};
+#pragma unroll
+        for (int w = 0; w < 4; w++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) diff = __dadd_rn(diff, div255[(d[w] >> (8 * k)) & 0xFFu]);
+    }
+    return (unsigned long long)__double_as_longlong(diff);
+}
+__device__ __noinline__ unsigned nvb_pair_score_v(const uint8_t *qrow, const uint8_t *frow, int nc)
+{
+    const uint4 *q = reinterpret_cast<const uint4 *>(qrow);
+    const uint4 *f = reinterpret_cast<const uint4 *>(frow);
+    uint32_t sum = 0;
+    for (int c = 0; c < nc; c++) {
+        const uint4 qq = q[c], ff = __ldg(f + c);
+        sum = nvb_sad4(qq.x, ff.x, sum); sum = nvb_sad4(qq.y, ff.y, sum);
+        sum = nvb_sad4(qq.z, ff.z, sum); sum = nvb_sad4(qq.w, ff.w, sum);
+    }
+    return sum;
+}
 __device__ __forceinline__ unsigned nvb_cand_sad(const StepArgs &a, int key)
 {
     return (unsigned)((a.sad_const + (key >> 8)) >> 1);   // key = -256 * dot + column, SAD = (C - dot) / 2
@@ -389,6 +421,7 @@ __device__ __forceinline__ void nvb_decide_cand(const StepArgs &a, int b, unsign
                                                 const double *div255)
 {
     const int tid = threadIdx.x;
+    const int nc = a.Ppad / 16;
     __shared__ unsigned s_minsad;
     __shared__ int s_ntied, s_njobs;
     __shared__ unsigned s_hsad[NVB_STEP_MAX_A_SMEM];
@@ -420,19 +453,16 @@ __device__ __forceinline__ void nvb_decide_cand(const StepArgs &a, int b, unsign
         unsigned long long eb = NVB_EXACT_NONE;
         if (s_hview[k] >= 0) {
             if (!(have_ties && s_hsad[k] == M)) {
-                eb = (unsigned long long)__double_as_longlong(
-                    nvb_exact_diff_rows(a, g * a.Ppad, (size_t)s_hview[k] * a.Ppad, div255));
+                eb = nvb_exact_bits(a.gv + g * a.Ppad, a.lv + (size_t)s_hview[k] * a.Ppad, nc, div255);
             } else {
                 const int2 *c = a.cand + g * a.n_vt;
                 for (int t = 0; t < a.n_vt; t++) {
                     const int2 kk = c[t];
                     if (kk.x == 0x7FFFFFFF || nvb_cand_sad(a, kk.x) != M) continue;
-                    unsigned long long e = (unsigned long long)__double_as_longlong(
-                        nvb_exact_diff_rows(a, g * a.Ppad, (size_t)(t * 256 + (kk.x & 255)) * a.Ppad, div255));
+                    unsigned long long e = nvb_exact_bits(a.gv + g * a.Ppad, a.lv + (size_t)(t * 256 + (kk.x & 255)) * a.Ppad, nc, div255);
                     eb = e < eb ? e : eb;
                     if (kk.y == 0x7FFFFFFF || nvb_cand_sad(a, kk.y) != M) continue;
-                    e = (unsigned long long)__double_as_longlong(
-                        nvb_exact_diff_rows(a, g * a.Ppad, (size_t)(t * 256 + (kk.y & 255)) * a.Ppad, div255));
+                    e = nvb_exact_bits(a.gv + g * a.Ppad, a.lv + (size_t)(t * 256 + (kk.y & 255)) * a.Ppad, nc, div255);
                     eb = e < eb ? e : eb;
                     // both of this tile's candidates tie: later views of the tile may tie as well
                     const int slot = atomicAdd(&s_njobs, 1);
@@ -441,8 +471,8 @@ __device__ __forceinline__ void nvb_decide_cand(const StepArgs &a, int b, unsign
                     } else {
                         for (int col = (kk.y & 255) + 1; col < 256 && t * 256 + col < a.N; col++) {
                             const size_t fo = (size_t)(t * 256 + col) * a.Ppad;
-                            if (nvb_pair_score(a, g * a.Ppad, fo) == M) {
-                                e = (unsigned long long)__double_as_longlong(nvb_exact_diff_rows(a, g * a.Ppad, fo, div255));
+                            if (nvb_pair_score_v(a.gv + g * a.Ppad, a.lv + fo, nc) == M) {
+                                e = nvb_exact_bits(a.gv + g * a.Ppad, a.lv + fo, nc, div255);
                                 eb = e < eb ? e : eb;
                             }
                         }
@@ -459,8 +489,8 @@ __device__ __forceinline__ void nvb_decide_cand(const StepArgs &a, int b, unsign
         const size_t g = (size_t)b * a.A + k;
         for (int col = s_jobs[j][2] + tid; col < 256 && t * 256 + col < a.N; col += blockDim.x) {
             const size_t fo = (size_t)(t * 256 + col) * a.Ppad;
-            if (nvb_pair_score(a, g * a.Ppad, fo) == M)
-                atomicMin(s_exact + k, (unsigned long long)__double_as_longlong(nvb_exact_diff_rows(a, g * a.Ppad, fo, div255)));
+            if (nvb_pair_score_v(a.gv + g * a.Ppad, a.lv + fo, nc) == M)
+                atomicMin(s_exact + k, nvb_exact_bits(a.gv + g * a.Ppad, a.lv + fo, nc, div255));
         }
     }
     __syncthreads();
