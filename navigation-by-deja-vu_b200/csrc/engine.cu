@@ -160,6 +160,11 @@ struct nvb_engine {
 
 // Step form for small un-sharded libraries, NAVSIM_B200_STEP_FORM (C2, warm, us per step-batch):
 //   3 (default)  K2 | decide | grid-wide tie pass | move + sample                          50.6
+//   5            K2 (tensor-core kernel keeping the two best views per view tile) | decide from those
+//                candidates + move + sample in ONE launch: no pass over the library for ties, two
+//                launches per step.  Measured with the tensor-core kernel (round 2): 35.7 us against
+//                33.9 us for form 3 -- the second-best tracking costs the distance kernel's epilogue
+//                2.5 us and the per-agent decision takes as long inside the big kernel as in its own
 //   4            K2 | decide | move + sample with the tie pass folded into its front       52.3
 //                (needs the whole move+sample grid co-resident, else form 3 is used; the agents
 //                with ties are the critical path either way, so only a launch boundary is saved
@@ -169,7 +174,7 @@ struct nvb_engine {
 static int step_form()
 {
     static const int v = getenv("NAVSIM_B200_STEP_FORM") ? atoi(getenv("NAVSIM_B200_STEP_FORM")) : 3;
-    return (v >= 1 && v <= 4) ? v : 3;
+    return (v >= 1 && v <= 5) ? v : 3;
 }
 
 static bool split_step() { return step_form() != 1; }
@@ -302,13 +307,12 @@ static bool use_tc(const nvb_engine *e, long long G)
 // best candidates per view tile + move + sample, step.cuh k3_move_sample<.., CAND>) instead of
 // decide | grid-wide tie pass | move + sample: small un-sharded libraries whose batch the
 // tensor-core kernel scores, sweeps of up to 512 headings, at most 64 view tiles.
-// NAVSIM_B200_NO_CAND=1 keeps the three-launch form.
+// Step form 5 (NAVSIM_B200_STEP_FORM=5); where it does not apply form 3 runs.
 static bool fused_step(const nvb_engine *e);
 static bool cand_form(const nvb_engine *e)
 {
-    static const bool off = getenv("NAVSIM_B200_NO_CAND") != nullptr;
-    return !off && fused_step(e) && use_tc(e, (long long)e->B * e->A) && e->lenc_valid && e->tc_lib_ok &&
-           e->A <= NVB_STEP_MAX_A_SMEM && (e->N + NVB_TC_NT - 1) / NVB_TC_NT <= 64 && step_form() == 3;
+    return step_form() == 5 && fused_step(e) && use_tc(e, (long long)e->B * e->A) && e->lenc_valid && e->tc_lib_ok &&
+           e->A <= NVB_STEP_MAX_A_SMEM && (e->N + NVB_TC_NT - 1) / NVB_TC_NT <= 64;
 }
 
 // Thermometer planes of the V-channel quantisation table (distance_tc.cuh): levels = the
@@ -1468,7 +1472,8 @@ static int launch_k31_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa,
 // agent) is resident at once -- its tie agents wait for work done by the other CTAs.
 static int effective_form(const nvb_engine *e)
 {
-    const int f = step_form();
+    int f = step_form();
+    if (f == 5) f = 3;   // (the candidate form is chosen by cand_form(); everything else runs as form 3)
     if (f == 4 && e->ms_capacity >= 0 && e->B > e->ms_capacity) return 3;
     return f;
 }
@@ -1851,7 +1856,7 @@ extern "C" int nvb_agents_step_io(nvb_engine *e, const double *poses_in, int nst
         // the move writes the results into the caller's buffers
         CK(cudaGraphLaunch(e->graph_zc, e->stream));
         e->glimpses_pending = false;
-        e->launches += fused_step(e) && step_form() < 3 ? 3 : 5;
+        e->launches += fused_step(e) && effective_form(e) < 3 ? 3 : 5;
         e->steps_done += 1;
         CK(cudaStreamSynchronize(e->stream));
         return NVB_OK;
@@ -1890,7 +1895,7 @@ extern "C" int nvb_agents_step_io(nvb_engine *e, const double *poses_in, int nst
             e->graph_dirty = false;
         } else {
             CK(cudaGraphLaunch(e->graph_io, e->stream));
-            e->launches += fused_step(e) && step_form() < 3 ? 3 : 5;
+            e->launches += fused_step(e) && effective_form(e) < 3 ? 3 : 5;
             e->steps_done += 1;
         }
     } else if ((rc = run_steps(e, nsteps, 0, 0, poses_in != nullptr))) {
