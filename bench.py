@@ -244,6 +244,18 @@ def run_ours(args):
         eng.set_distance_kernel(simd_only=False)
         eng.rewind()
 
+    # ---- the same distance kernel on 16x the agents of the same world: how far the kernel gets
+    # once the problem is large enough to fill the machine (C2 itself is 2.8 us of tensor work)
+    big = None
+    if not args.quick:
+        poses16 = np.tile(poses, (16, 1))
+        eng.set_agents(poses16)
+        eng.step(2)
+        eng.sync()
+        big_ms = eng.time_distance_kernel(10)
+        big = {"agents": len(poses16), "kernel": eng.distance_kernel, "launch_ms_alone": big_ms}
+        eng.set_agents(poses)
+
     # ---- e2e: per step pinned host poses in, results out, one sync
     h_in = torch.empty((B, 3), dtype=torch.float64).pin_memory()
     h_pose = torch.empty((B, 3), dtype=torch.float64).pin_memory()
@@ -302,6 +314,12 @@ def run_ours(args):
             "launch_ms": k2_s * 1e3, "launch_ms_alone": k2_alone_ms, "launches_timed": k2_n,
             "launch_ms_in_graph": k2_graph_ms,
             "frac_in_graph": (ops / (k2_graph_ms * 1e-3) / 1e12) / (2.0 * bf16) if k2_graph_ms else None,
+            "at_16x_agents": None if big is None else {
+                "agents": big["agents"], "launch_ms_alone": big["launch_ms_alone"],
+                "achieved": 16.0 * ops / (big["launch_ms_alone"] * 1e-3) / 1e12,
+                "frac": 16.0 * ops / (big["launch_ms_alone"] * 1e-3) / 1e12 / (2.0 * bf16),
+                "frac_of_int8_probe": 16.0 * ops / (big["launch_ms_alone"] * 1e-3) / mma_peak if mma_peak and mma_peak > 0 else None,
+                "note": "same world and library, 16 x the agents (G = 163840 glimpses): the kernel when the problem fills the machine"},
             "byte_simd_kernel": {
                 "kernel": "k2_sad_v", "launch_ms_alone": simd_alone_ms,
                 "int_alu_TOPs": 2.0 * B * A * N * P / (simd_alone_ms * 1e-3) / 1e12 if simd_alone_ms else None,
@@ -370,6 +388,11 @@ def run_ours(args):
 
     if world == 1 and rank == 0 and not args.no_cpu and not args.quick:
         line["cpu_baseline"] = cpu_baseline(wl, target_seconds=args.cpu_seconds, cores=args.cores)
+    if world == 1 and rank == 0 and not args.quick:
+        try:
+            line["c1_dropin"] = c1_dropin_record(L, tpath, kw)
+        except Exception as e:
+            line["c1_dropin"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if world > 1 and not args.quick:
         # the one configuration with a real exchange step (BASELINE configs[3]): a 10^6-view
         # library sharded by view over the ranks, MIN exchange over NVLink peer memory
@@ -384,6 +407,49 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- C1 through the API
+def c1_dropin_record(L, tpath, kw):
+    """BASELINE configs[0] the way scripts/run_experiment.py drives it: one agent,
+    NavBySceneFamiliarity.step_forward() once per frame for a whole trajectory -- the product
+    class (device run-ahead of 64 steps, replayed per call) and, when oracle/_ref is there,
+    the compiled reference on one host core, same world and start pose."""
+    import warnings
+    import navsim
+    from navsim import synthetic
+    pose = synthetic.start_pose(tpath, (0.05, 3.0), 80)
+    frames = synthetic.default_frames(tpath, kw["step_size"])
+
+    def drive(mod, nsf):
+        nsf.train_from_path(tpath)
+        nsf.position = (pose[0], pose[1])
+        nsf.angle = pose[2]
+        done, status = 0, 0
+        t0 = time.perf_counter()
+        try:
+            for _ in range(frames):
+                nsf.step_forward()
+                done += 1
+        except mod.StopNavigationException as e:
+            status = e.get_code()
+        return done, status, time.perf_counter() - t0, tuple(nsf.position)
+
+    make = lambda: navsim.NavBySceneFamiliarity(L, familiarity_model=navsim.sads_familiarity(0.0), **kw)   # noqa: E731
+    drive(navsim, make())
+    d1, s1, t1, p1 = drive(navsim, make())
+    rec = {"workload": "C1: reference defaults, one agent, nsf.step_forward() per frame (frame budget %d)" % frames,
+           "frames_completed": d1, "stop_status": s1, "us_per_step_forward": t1 / max(d1, 1) * 1e6,
+           "agent_steps_per_sec": d1 / t1, "comparisons_per_sec": d1 * kw["n_test_angles"] * len(tpath) / t1}
+    from oracle import ref_loader
+    ref = ref_loader.load_reference()
+    if ref is not None:
+        warnings.filterwarnings("ignore")
+        d2, s2, t2, p2 = drive(ref, ref.NavBySceneFamiliarity(L, familiarity_model=ref.util.sads_familiarity(0.0), **kw))
+        rec["reference_one_core"] = {"us_per_step_forward": t2 / max(d2, 1) * 1e6, "frames_completed": d2,
+                                     "stop_status": s2, "kind": "reference"}
+        rec["same_trajectory_as_reference"] = bool(d1 == d2 and s1 == s2 and p1 == p2)
+    return rec
 
 
 # --------------------------------------------------------------------------- view shards
@@ -418,7 +484,7 @@ def c4_library(c4, genuine, n_total):
     return scenes
 
 
-def view_sharded_record(rank, world, local, dist, agents=(1, 64), steps=20, views=None):
+def view_sharded_record(rank, world, local, dist, agents=(1, 64, 1024), steps=20, views=None):
     """Every rank holds the landscape, all agents and a contiguous slice of the library; the
     per-step MIN exchanges run inside the decide / move kernels over NVLink peer memory.  The
     same rank also runs the WHOLE library unsharded: heading log and poses must be identical."""
