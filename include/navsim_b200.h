@@ -222,6 +222,24 @@ int nvb_debug_step_clocks(nvb_engine *e, long long *out);
  * out [4][2048][3], ns, of the last step-batch; 0 = CTA not present. */
 int nvb_debug_timeline(nvb_engine *e, int nsteps, long long *out);
 
+/* ---- landscape preparation on the device ------------------------------------------------
+ * What make_nsf does per landscape / trial on the host (scripts/run_experiment.py:160-199,
+ * navsim/util.pyx:76-88 set_HS_where_equal), on the landscape the engine holds:
+ * label_grains: threshold V >= `threshold`, modal filter with a modal_w x modal_w footprint
+ *   (odd; 0 or 1: none; skimage.filters.rank.modal on the 0/1 image), 8-connected components
+ *   numbered in raster order of their first pixel (skimage.measure.label); returns the count.
+ * grains_get:   per-grain pixel counts (regionprops area; equivalent_diameter = sqrt(4 area / pi))
+ *   and / or the label image [rows][cols] int64 (0 = background); either pointer may be NULL.
+ * paint:        H and S of every labelled pixel from per-grain tables (set_HS_where_equal).
+ * flip:         landscape[::-1] / [:, ::-1] (run_experiment.py:196-199); labels are dropped.
+ * download:     the landscape as [rows][cols][3] uint8 (tests).
+ * Painting and flipping invalidate the library and the agents. */
+int nvb_landscape_label_grains(nvb_engine *e, int threshold, int modal_w, int64_t *n_grains);
+int nvb_landscape_grains_get(nvb_engine *e, int32_t *areas, int64_t *labels);
+int nvb_landscape_paint(nvb_engine *e, const uint8_t *H, const uint8_t *S, int64_t n_grains);
+int nvb_landscape_flip(nvb_engine *e, int flip_v, int flip_h);
+int nvb_landscape_download(nvb_engine *e, uint8_t *hsv);
+
 /* Which distance kernel scores the glimpses.  mode 0 (default): the tensor-core kernel
  * (tcgen05 int8, exact thermometer form of the sum of absolute differences) whenever the V
  * quantisation has at most 9 levels, chem_weight is 0 and the batch has at least 96

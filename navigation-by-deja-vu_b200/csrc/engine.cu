@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "distance.cuh"
 #include "distance_tc.cuh"
+#include "landscape.cuh"
 #include "sampler.cuh"
 #include "step.cuh"
 
@@ -111,6 +112,10 @@ struct nvb_engine {
     int span_tc_key[3] = {-1, -1, -1};
     int2 *d_cand = nullptr;         // [Gcap][n_vt] two best candidates per glimpse and view tile (TOP2 kernel)
     long long cand_cap = 0;
+    // landscape preparation (landscape.cuh): grain labels of the current landscape
+    long long *d_labels = nullptr;
+    int *d_grain_area = nullptr;
+    long long n_grains = -1;        // -1: not labelled
     // view-sharded library over NVLink peer memory
     unsigned long long *d_xarea = nullptr;
     P2PArgs p2p{};
@@ -503,7 +508,7 @@ extern "C" void nvb_engine_destroy(nvb_engine *e)
                     e->ag.budget, e->ag.nav_frames, e->ag.err_sum, e->ag.err_n, e->ag.coverage,
                     e->ag.stepped, e->d_step, e->log_best, e->log_pose, e->log_sfam, e->log_afam,
                     e->d_poses0, e->d_budget0, e->d_spans, e->d_pending, e->d_dmin2, e->d_pblk,
-                    e->d_tc_tab, e->d_tc_level_of, e->d_genc, e->d_lenc, e->d_spans_tc, e->d_tc_bad, e->d_cand};
+                    e->d_tc_tab, e->d_tc_level_of, e->d_genc, e->d_lenc, e->d_spans_tc, e->d_tc_bad, e->d_cand, e->d_labels, e->d_grain_area};
     for (int i = 0; i < NVB_P2P_MAX_RANKS; i++)
         if (e->p2p_opened[i]) cudaIpcCloseMemHandle(e->p2p_opened[i]);
     free_dev(e->d_xarea); free_dev(e->d_p2p_seq); free_dev(e->d_p2p_err);
@@ -547,7 +552,127 @@ extern "C" int nvb_set_landscape(nvb_engine *e, const uint8_t *hsv, int rows, in
     if (rc) return rc;
     CK(cudaMemcpy(e->d_land, planar.data(), planar.size(), cudaMemcpyHostToDevice));
     e->rows = rows; e->cols = cols; e->pitch = pitch;
+    e->n_grains = -1;
     return rebuild_tmap(e);
+}
+
+// ---- landscape preparation on the device (landscape.cuh) ------------------
+extern "C" int nvb_landscape_label_grains(nvb_engine *e, int threshold, int modal_w, int64_t *n_grains)
+{
+    if (!e->d_land) return fail(NVB_E_INVALID, "no landscape");
+    if (modal_w < 0 || (modal_w > 0 && modal_w % 2 == 0)) return fail(NVB_E_INVALID, "modal footprint must be odd (or 0 for none)");
+    CK(cudaSetDevice(e->device));
+    const int rows = e->rows, cols = e->cols;
+    const long long n = (long long)rows * cols;
+    if (n >= (1ll << 31)) return fail(NVB_E_INVALID, "landscape too large to label");
+    uint8_t *d_m0 = nullptr, *d_m1 = nullptr;
+    int *d_parent = nullptr, *d_newid = nullptr, *d_rows = nullptr;
+    CK(cudaMalloc(&d_m0, (size_t)n));
+    CK(cudaMalloc(&d_m1, (size_t)n));
+    CK(cudaMalloc(&d_parent, sizeof(int) * (size_t)n));
+    CK(cudaMalloc(&d_newid, sizeof(int) * (size_t)n));
+    CK(cudaMalloc(&d_rows, sizeof(int) * (size_t)rows));
+    const dim3 g2((cols + 127) / 128, rows), b2(128);
+    const unsigned g1 = (unsigned)((n + 255) / 256);
+    k_ls_threshold<<<g2, b2, 0, e->stream>>>(e->d_land + 2 * (size_t)e->pitch * rows, rows, cols, e->pitch, threshold, d_m0);
+    const uint8_t *mask = d_m0;
+    if (modal_w > 1) {
+        k_ls_modal<<<g2, b2, 0, e->stream>>>(d_m0, rows, cols, modal_w, d_m1);
+        mask = d_m1;
+    }
+    k_ls_init<<<g1, 256, 0, e->stream>>>(mask, n, d_parent);
+    k_ls_link<<<g2, b2, 0, e->stream>>>(mask, rows, cols, d_parent);
+    k_ls_flatten<<<g1, 256, 0, e->stream>>>(n, d_parent);
+    k_ls_row_roots<<<rows, 128, 0, e->stream>>>(d_parent, rows, cols, d_rows);
+    e->launches += 6;
+    std::vector<int> rc(rows), off(rows);
+    CK(cudaMemcpyAsync(rc.data(), d_rows, sizeof(int) * rows, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    long long total = 0;
+    for (int y = 0; y < rows; y++) { off[y] = (int)total; total += rc[y]; }
+    CK(cudaMemcpyAsync(d_rows, off.data(), sizeof(int) * rows, cudaMemcpyHostToDevice, e->stream));
+    k_ls_number<<<rows, 32, 0, e->stream>>>(d_parent, rows, cols, d_rows, d_newid);
+    int rcode;
+    if ((rcode = alloc_dev(&e->d_labels, (size_t)n))) return rcode;
+    if ((rcode = alloc_dev(&e->d_grain_area, (size_t)(total > 0 ? total : 1)))) return rcode;
+    CK(cudaMemsetAsync(e->d_grain_area, 0, sizeof(int) * (size_t)(total > 0 ? total : 1), e->stream));
+    k_ls_relabel<<<g1, 256, 0, e->stream>>>(d_parent, d_newid, n, e->d_labels, e->d_grain_area);
+    e->launches += 2;
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    cudaFree(d_m0); cudaFree(d_m1); cudaFree(d_parent); cudaFree(d_newid); cudaFree(d_rows);
+    e->n_grains = total;
+    if (n_grains) *n_grains = total;
+    return NVB_OK;
+}
+
+extern "C" int nvb_landscape_grains_get(nvb_engine *e, int32_t *areas, int64_t *labels)
+{
+    if (e->n_grains < 0) return fail(NVB_E_INVALID, "grains not labelled");
+    CK(cudaSetDevice(e->device));
+    if (areas && e->n_grains > 0)
+        CK(cudaMemcpyAsync(areas, e->d_grain_area, sizeof(int32_t) * (size_t)e->n_grains, cudaMemcpyDeviceToHost, e->stream));
+    if (labels)
+        CK(cudaMemcpyAsync(labels, e->d_labels, sizeof(int64_t) * (size_t)e->rows * e->cols, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return NVB_OK;
+}
+
+extern "C" int nvb_landscape_paint(nvb_engine *e, const uint8_t *H, const uint8_t *S, int64_t n_grains)
+{
+    if (e->n_grains < 0) return fail(NVB_E_INVALID, "grains not labelled");
+    if (n_grains != e->n_grains) return fail(NVB_E_INVALID, "%lld table entries for %lld grains", (long long)n_grains, e->n_grains);
+    if (n_grains == 0) return NVB_OK;
+    CK(cudaSetDevice(e->device));
+    e->graph_dirty = true;
+    uint8_t *d_t = nullptr;
+    CK(cudaMalloc(&d_t, (size_t)2 * n_grains));
+    CK(cudaMemcpyAsync(d_t, H, (size_t)n_grains, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(d_t + n_grains, S, (size_t)n_grains, cudaMemcpyHostToDevice, e->stream));
+    k_ls_paint<<<dim3((e->cols + 127) / 128, e->rows), 128, 0, e->stream>>>(e->d_labels, e->rows, e->cols, e->pitch,
+                                                                             (long long)e->pitch * e->rows, d_t, d_t + n_grains, e->d_land);
+    e->launches++;
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d_t);
+    e->N = 0; e->B = 0;     // the library was sampled from the old pixels
+    return NVB_OK;
+}
+
+extern "C" int nvb_landscape_flip(nvb_engine *e, int flip_v, int flip_h)
+{
+    if (!e->d_land) return fail(NVB_E_INVALID, "no landscape");
+    if (!flip_v && !flip_h) return NVB_OK;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    e->graph_dirty = true;
+    uint8_t *d_new = nullptr;
+    const size_t bytes = (size_t)3 * e->pitch * e->rows;
+    CK(cudaMalloc(&d_new, bytes));
+    CK(cudaMemsetAsync(d_new, 0, bytes, e->stream));
+    k_ls_flip_planes<<<dim3((e->cols + 127) / 128, e->rows, 3), 128, 0, e->stream>>>(e->d_land, e->rows, e->cols, e->pitch,
+                                                                                     (long long)e->pitch * e->rows, flip_v, flip_h, d_new);
+    e->launches++;
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_land);
+    e->d_land = d_new;
+    e->n_grains = -1;       // labels refer to the unflipped pixels
+    e->N = 0; e->B = 0;
+    return rebuild_tmap(e);
+}
+
+extern "C" int nvb_landscape_download(nvb_engine *e, uint8_t *hsv)
+{
+    if (!e->d_land) return fail(NVB_E_INVALID, "no landscape");
+    CK(cudaSetDevice(e->device));
+    std::vector<uint8_t> planar((size_t)3 * e->pitch * e->rows);
+    CK(cudaMemcpyAsync(planar.data(), e->d_land, planar.size(), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int ch = 0; ch < 3; ch++)
+        for (int y = 0; y < e->rows; y++) {
+            const uint8_t *src = planar.data() + ((size_t)ch * e->rows + y) * e->pitch;
+            for (int x = 0; x < e->cols; x++) hsv[((size_t)y * e->cols + x) * 3 + ch] = src[x];
+        }
+    return NVB_OK;
 }
 
 extern "C" int nvb_set_sensor(nvb_engine *e, int W, int H, int pw, int ph, const uint8_t *lut,

@@ -28,6 +28,11 @@ SIGNATURES = {
     "nvb_sync": (_i, [_vp]),
     "nvb_stream_handle": (_vp, [_vp]),
     "nvb_set_landscape": (_i, [_vp, _vp, _i, _i, _sz, _sz, _sz]),
+    "nvb_landscape_label_grains": (_i, [_vp, _i, _i, C.POINTER(_i64)]),
+    "nvb_landscape_grains_get": (_i, [_vp, _vp, _vp]),
+    "nvb_landscape_paint": (_i, [_vp, _vp, _vp, _i64]),
+    "nvb_landscape_flip": (_i, [_vp, _i, _i]),
+    "nvb_landscape_download": (_i, [_vp, _vp]),
     "nvb_set_sensor": (_i, [_vp, _i, _i, _i, _i, _vp, _i]),
     "nvb_set_saccade": (_i, [_vp, _i, _vp]),
     "nvb_set_nav_params": (_i, [_vp, _d, _d, _d, _d, _d]),

@@ -69,6 +69,56 @@ class NavEngine(object):
         self.n_agents = 0
         self._familiar_scenes = None
 
+    # ---- landscape preparation on the device (scripts/run_experiment.py:160-199) ----------
+    def label_grains(self, threshold=200, min_chem_grain_diameter=2):
+        """Threshold + modal filter + grain labelling of the landscape on the device, as make_nsf
+        does them (run_experiment.py:169-180).  Returns the per-grain pixel counts (int32)."""
+        w = min_chem_grain_diameter // 2                   # :170-174
+        if not w == 0:
+            if w % 2 == 0:
+                w -= 1
+            w = int(w)
+        n = C.c_int64(0)
+        check(self._lib.nvb_landscape_label_grains(self._h, int(threshold), int(w), C.byref(n)))
+        areas = np.zeros(int(n.value), np.int32)
+        check(self._lib.nvb_landscape_grains_get(self._h, ptr(areas) if len(areas) else None, None))
+        return areas
+
+    def grain_labels(self):
+        out = np.empty(self.landscape.shape[:2], np.int64)
+        check(self._lib.nvb_landscape_grains_get(self._h, None, ptr(out)))
+        return out
+
+    def add_chemistry(self, areas, n_chemicals=2, min_grain_diameter=2, concentration_range=(127, 128), rng=None):
+        """add_chemistry (run_experiment.py:126-142) on the device copy of the landscape: per-grain
+        hue / saturation tables drawn on the host (same RNG calls), painted by a kernel."""
+        rng = np.random.default_rng() if rng is None else rng
+        n = len(areas)
+        chems = rng.integers(n_chemicals, size=n, dtype=np.uint8) * np.uint8(255 // n_chemicals)
+        sats = rng.integers(concentration_range[0], concentration_range[1], size=n, dtype=np.uint8)
+        sats[np.sqrt(4.0 * areas / np.pi) < min_grain_diameter] = 0      # regionprops equivalent_diameter
+        chems, sats = np.ascontiguousarray(chems, np.uint8), np.ascontiguousarray(sats, np.uint8)
+        check(self._lib.nvb_landscape_paint(self._h, ptr(chems), ptr(sats), n))
+        self._after_landscape_edit()
+        return chems, sats
+
+    def flip_landscape(self, vertical=False, horizontal=False):
+        """landscape[::-1] / [:, ::-1] on the device (run_experiment.py:196-199)."""
+        check(self._lib.nvb_landscape_flip(self._h, int(bool(vertical)), int(bool(horizontal))))
+        self._after_landscape_edit()
+
+    def download_landscape(self):
+        out = np.empty(self.landscape.shape[:2] + (3,), np.uint8)
+        check(self._lib.nvb_landscape_download(self._h, ptr(out)))
+        return out
+
+    def _after_landscape_edit(self):
+        self.training_path = None
+        self.n_views = 0
+        self.n_agents = 0
+        self._familiar_scenes = None
+        self.landscape = self.download_landscape() if False else self.landscape   # host copy is the caller's; shape only
+
     def set_world(self, sensor_dimensions, step_size, n_test_angles=60, sensor_pixel_dimensions=[1, 1],
                   max_distance_to_training_path=np.inf, n_sensor_levels=5, mask_middle_n=0,
                   threshold_factor=2., coverage_threshold_factor=0.8, saccade_degrees=180., chem_weight=0.0):
