@@ -78,6 +78,7 @@ struct nvb_engine {
     uint8_t *d_lh = nullptr, *d_ls = nullptr, *d_lv = nullptr;
     double *d_path = nullptr;
     double *d_pblk = nullptr;       // [ceil(n_path / 16)][4]: bounding circle (cx, cy, r, -) of 16 consecutive path points
+    double *d_pblk2 = nullptr;      // [ceil(blocks / 64)][4]: the same for groups of 64 blocks (long paths)
     int n_path = 0;
     long long view_offset = 0, n_total = 0;
     // glimpse buffers
@@ -507,7 +508,7 @@ extern "C" void nvb_engine_destroy(nvb_engine *e)
                     e->d_tie_items, e->d_tie_thr, e->d_tie_next, e->d_tie_ready, e->ag.poses, e->ag.status, e->ag.completed,
                     e->ag.budget, e->ag.nav_frames, e->ag.err_sum, e->ag.err_n, e->ag.coverage,
                     e->ag.stepped, e->d_step, e->log_best, e->log_pose, e->log_sfam, e->log_afam,
-                    e->d_poses0, e->d_budget0, e->d_spans, e->d_pending, e->d_dmin2, e->d_pblk,
+                    e->d_poses0, e->d_budget0, e->d_spans, e->d_pending, e->d_dmin2, e->d_pblk, e->d_pblk2,
                     e->d_tc_tab, e->d_tc_level_of, e->d_genc, e->d_lenc, e->d_spans_tc, e->d_tc_bad, e->d_cand, e->d_labels, e->d_grain_area};
     for (int i = 0; i < NVB_P2P_MAX_RANKS; i++)
         if (e->p2p_opened[i]) cudaIpcCloseMemHandle(e->p2p_opened[i]);
@@ -1198,6 +1199,23 @@ static int set_path(nvb_engine *e, const double *path, int n)
     }
     if ((rc = alloc_dev(&e->d_pblk, (size_t)4 * nb))) return rc;
     CK(cudaMemcpy(e->d_pblk, blk.data(), sizeof(double) * 4 * nb, cudaMemcpyHostToDevice));
+    // second level for long paths: one circle per NVB_PATH_GROUP blocks
+    const int ng = (nb + NVB_PATH_GROUP - 1) / NVB_PATH_GROUP, gpts = NVB_PATH_GROUP * NVB_PATH_BLOCK;
+    std::vector<double> grp((size_t)4 * ng);
+    for (int j = 0; j < ng; j++) {
+        const int n0 = j * gpts, n1 = n0 + gpts < n ? n0 + gpts : n;
+        double cx = 0, cy = 0;
+        for (int i = n0; i < n1; i++) { cx += path[2 * i]; cy += path[2 * i + 1]; }
+        cx /= (n1 - n0); cy /= (n1 - n0);
+        double r = 0;
+        for (int i = n0; i < n1; i++) {
+            const double d = hypot(path[2 * i] - cx, path[2 * i + 1] - cy);
+            if (d > r) r = d;
+        }
+        grp[4 * j] = cx; grp[4 * j + 1] = cy; grp[4 * j + 2] = r * (1.0 + 1e-12) + 1e-9; grp[4 * j + 3] = 0.0;
+    }
+    if ((rc = alloc_dev(&e->d_pblk2, (size_t)4 * ng))) return rc;
+    CK(cudaMemcpy(e->d_pblk2, grp.data(), sizeof(double) * 4 * ng, cudaMemcpyHostToDevice));
     return NVB_OK;
 }
 
@@ -1505,6 +1523,7 @@ static StepArgs make_step_args(nvb_engine *e, int fake, int log_afam)
     s.lv = e->d_lv; s.lh = e->d_lh; s.ls = e->d_ls;
     s.path = e->d_path; s.n_path = e->n_path;
     s.pblk = getenv("NAVSIM_B200_NO_PATH_BLOCKS") ? nullptr : e->d_pblk;
+    s.pblk2 = s.pblk ? e->d_pblk2 : nullptr;
     s.view_offset = e->view_offset;
     s.keys = e->d_keys; s.exact = e->d_exact;
     s.idx_bits = (e->cw == 0.0) ? 32 : 28;
@@ -1717,10 +1736,20 @@ static int phase2(nvb_engine *e, const StepArgs &s)
     return NVB_OK;
 }
 
+// update_error over a long training path: with the two-level bounding circles the agent's own
+// CTA prunes it (step.cuh); the grid-wide three-kernel scan remains for the cases the prefilter
+// does not cover (circles switched off, or a coverage threshold above max_distance).
+static bool long_path_split(const nvb_engine *e)
+{
+    static const bool no_blocks = getenv("NAVSIM_B200_NO_PATH_BLOCKS") != nullptr;
+    const bool one_pass = e->cvf * e->step_size <= e->max_dist;
+    return e->n_path > NVB_PATH_SPLIT && (no_blocks || !one_pass);
+}
+
 static int phase3(nvb_engine *e, const StepArgs &s)
 {
     // (view shards over NVLink: the move's prologue MINs the exact differences over the ranks)
-    if (e->n_path > NVB_PATH_SPLIT && !s.fake) {
+    if (long_path_split(e) && !s.fake) {
         // long training path: pose update | grid-wide distance scan | bookkeeping
         const int chunks = (e->n_path + NVB_PATH_CHUNK - 1) / NVB_PATH_CHUNK;
         CK(launch_seq(k3_move_pose, dim3(e->B), dim3(NVB_STEP_THREADS), 0, e->stream, s));
@@ -1768,8 +1797,12 @@ static int launch_distance_timed(nvb_engine *e, int G)
 static bool fused_step(const nvb_engine *e)
 {
     static const bool off = getenv("NAVSIM_B200_NO_FUSED_STEP") != nullptr;
-    return e->view_offset == 0 && e->n_total == e->N && e->N <= NVB_FUSED_STEP_MAX_VIEWS &&
-           sampler_slices(e) == 1 && !off;
+    // forms 1 and 2 rescan the library inside the agent's own CTA for ties: small un-sharded
+    // libraries only.  Forms 3+ (grid-wide tie pass) take any library, sharded ones included
+    // (the exchanges sit in the prologues of decide and of move+sample), unless update_error
+    // needs the grid-wide path scan.
+    const bool small = e->view_offset == 0 && e->n_total == e->N && e->N <= NVB_FUSED_STEP_MAX_VIEWS;
+    return (small || (step_form() >= 3 && !long_path_split(e))) && sampler_slices(e) == 1 && !off;
 }
 
 // One step-batch.  Small un-sharded libraries (fused form): K2, then ONE launch that
@@ -1863,7 +1896,7 @@ static int run_steps(nvb_engine *e, int nsteps, int fake, int log_afam, bool eag
         // (+2 for the long-path move, +2 for the NVLink exchanges)
         const int ef = effective_form(e);
         const int per_step = fused_step(e) ? ((cand_form(e) && e->d_cand) ? 2 : ef == 3 ? 4 : (ef == 2 || ef == 4) ? 3 : 2)
-                                           : 5 + (e->n_path > NVB_PATH_SPLIT && !fake ? 2 : 0) ;
+                                           : 5 + (long_path_split(e) && !fake ? 2 : 0);
         for (int i = done; i < nsteps; i++) {
             CK(cudaGraphLaunch(e->graph_exec, e->stream));
             e->launches += per_step;

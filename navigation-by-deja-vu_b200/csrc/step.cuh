@@ -148,6 +148,7 @@ struct StepArgs {
     int pdl_early;               // trigger the dependent launch at the top of every kernel
     long long *tl;               // tuning aid: timeline stamps (nvb_tl_stamp) or nullptr
     const double *pblk;          // [ceil(n_path / NVB_PATH_BLOCK)][4] bounding circles of path blocks, or nullptr
+    const double *pblk2;         // [ceil(blocks / NVB_PATH_GROUP)][4] bounding circles of groups of blocks (long paths), or nullptr
     // host-driven form without copy operations: results of the step written straight into the
     // caller's page-locked buffers (device-mapped); each nullptr when not wanted
     int16_t *out_best;           // [B]
@@ -162,7 +163,9 @@ struct StepArgs {
 };
 
 #define NVB_PATH_BLOCK 16      /* path points per bounding circle (update_error prefilter) */
-#define NVB_PATH_LIVE_MAX 1024  /* blocks the prefilter can list: paths up to NVB_PATH_SPLIT points */
+#define NVB_PATH_LIVE_MAX 1024  /* blocks the prefilter can list */
+#define NVB_PATH_GROUP 64       /* blocks per second-level group (long paths) */
+#define NVB_PATH_GRP_MAX 16     /* second-level groups the prefilter can list */
 #define NVB_STEP_THREADS 128   /* == NVB_SAMPLER_THREADS: k31_step_sample runs both bodies */
 #define NVB_STEP_MAX_A_SMEM 512 /* headings whose exact differences are kept in shared memory */
 #define NVB_TIE_Q_CHUNKS 64     /* fused tie scan: glimpse rows up to 1 KB are staged in shared memory */
@@ -646,60 +649,109 @@ __device__ __forceinline__ bool nvb_move(const StepArgs &a, int b, const unsigne
     double m = __longlong_as_double(0x7FF0000000000000ll);
     if (MODE == 2) {
         m = __longlong_as_double((long long)a.dmin2[b]);
-    } else if (a.pblk != nullptr && one_pass && a.n_path <= NVB_PATH_LIVE_MAX * NVB_PATH_BLOCK) {
+    } else if (a.pblk != nullptr && one_pass) {
         // Prefilter: a block of 16 consecutive path points lies inside a circle (c, r).  Its
         // points are no nearer than |p - c| - r and one of them is no farther than |p - c| + r.
         // With U = the smallest such upper bound, the nearest point and every point within
         // thr (coverage) sit in blocks whose lower bound is <= max(U, thr); only those blocks
         // are scanned, with exactly the arithmetic of the full scan, so the minimum and the
-        // coverage marks are the same.  (The scanning warps meet at a named barrier: warp 1
-        // may be busy with the rotations.)
+        // coverage marks are the same.  Long paths (more than NVB_PATH_LIVE_MAX blocks) get a
+        // second level first: groups of NVB_PATH_GROUP blocks with their own circles
+        // (a.pblk2), the same argument applied twice -- update_error over 10^6 path points then
+        // costs this CTA what it costs over 10^3.  Lists that overflow (a degenerate path with
+        // thousands of points on one spot near the agent) fall back to scanning everything.
+        // (The scanning warps meet at a named barrier: warp 1 may be busy with the rotations.)
         __shared__ double s_ub[8];
-        __shared__ unsigned short s_live[NVB_PATH_LIVE_MAX];
-        __shared__ int s_nlive;
+        __shared__ int s_live[NVB_PATH_LIVE_MAX];
+        __shared__ int s_grp[NVB_PATH_GRP_MAX];
+        __shared__ int s_nlive, s_ngrp;
         const int n_blk = (a.n_path + NVB_PATH_BLOCK - 1) / NVB_PATH_BLOCK;
+        const bool two_level = n_blk > NVB_PATH_LIVE_MAX && a.pblk2 != nullptr;
+        const int n_grp = (n_blk + NVB_PATH_GROUP - 1) / NVB_PATH_GROUP;
         const bool scanning = !warp1;
         const int sid = (!W1_HOOK || tid < 32) ? tid : tid - 32;   // index among the scanning threads
-        if (scanning) {
-            if (sid == 0) s_nlive = 0;
-            double ub = __longlong_as_double(0x7FF0000000000000ll);
-            for (int j = sid; j < n_blk; j += scan_n) {
-                const double2 cc = __ldg(reinterpret_cast<const double2 *>(a.pblk) + 2 * j);
-                const double2 cr = __ldg(reinterpret_cast<const double2 *>(a.pblk) + 2 * j + 1);
-                const double3 c = make_double3(cc.x, cc.y, cr.x);
-                const double ex = __dsub_rn(c.x, x), ey = __dsub_rn(c.y, y);
-                const double dc = __dsqrt_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
-                ub = fmin(ub, __dadd_rn(dc, c.z));
-            }
+        const int n_scan_warps = (int)(blockDim.x >> 5);
+        bool full_scan = n_blk > NVB_PATH_LIVE_MAX && !two_level;
+        // (cx, cy, r) of circle j of a level; lower / upper bound of the distances of its points
+        auto circle = [&](const double *tab, int j, double &lo, double &hi) {
+            const double2 cc = __ldg(reinterpret_cast<const double2 *>(tab) + 2 * j);
+            const double2 cr = __ldg(reinterpret_cast<const double2 *>(tab) + 2 * j + 1);
+            const double ex = __dsub_rn(cc.x, x), ey = __dsub_rn(cc.y, y);
+            const double dc = __dsqrt_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
+            hi = __dadd_rn(dc, cr.x);
+            lo = __dsub_rn(__dsub_rn(dc, cr.x), 1e-9 * (1.0 + dc));   // slack far above the rounding of dc and of the comparison
+        };
+        // block-wide minimum of `v` over the scanning warps
+        auto scan_min = [&](double v) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ub = fmin(ub, __shfl_xor_sync(0xFFFFFFFFu, ub, o));
-            if ((tid & 31) == 0) s_ub[tid >> 5] = ub;
+            for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+            asm volatile("bar.sync 1, %0;" ::"r"(scan_n) : "memory");   // s_ub free again
+            if ((tid & 31) == 0) s_ub[tid >> 5] = v;
             asm volatile("bar.sync 1, %0;" ::"r"(scan_n) : "memory");
-            // U = max(thr, min over the scanning warps of their upper bounds)
-            double umin = __longlong_as_double(0x7FF0000000000000ll);
-            for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++)
-                if (!(W1_HOOK && wq == 1)) umin = fmin(umin, s_ub[wq]);
-            const double U = fmax(thr, umin);
-            for (int j = sid; j < n_blk; j += scan_n) {
-                const double2 cc = __ldg(reinterpret_cast<const double2 *>(a.pblk) + 2 * j);
-                const double2 cr = __ldg(reinterpret_cast<const double2 *>(a.pblk) + 2 * j + 1);
-                const double3 c = make_double3(cc.x, cc.y, cr.x);
-                const double ex = __dsub_rn(c.x, x), ey = __dsub_rn(c.y, y);
-                const double dc = __dsqrt_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
-                // slack far above the rounding of dc and of the comparison
-                if (__dsub_rn(dc, c.z) <= __dadd_rn(U, 1e-9 * (1.0 + dc))) s_live[atomicAdd(&s_nlive, 1)] = (unsigned short)j;
-            }
-            asm volatile("bar.sync 1, %0;" ::"r"(scan_n) : "memory");
-            const int n_live = s_nlive;
-            for (int idx = sid; idx < n_live * NVB_PATH_BLOCK; idx += scan_n) {
-                const int n = (int)s_live[idx / NVB_PATH_BLOCK] * NVB_PATH_BLOCK + (idx % NVB_PATH_BLOCK);
-                if (n < a.n_path) {
-                    const double2 pt = __ldg(path + n);
-                    const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
-                    const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                    m = fmin(m, d2);
-                    if (d2 <= thr2) a.ag.coverage[(size_t)b * a.n_path + n] = 1;
+            double r = __longlong_as_double(0x7FF0000000000000ll);
+            for (int wq = 0; wq < n_scan_warps; wq++)
+                if (!(W1_HOOK && wq == 1)) r = fmin(r, s_ub[wq]);
+            return r;
+        };
+        if (scanning && !full_scan) {
+            if (sid == 0) { s_nlive = 0; s_ngrp = 0; }
+            const double inf = __longlong_as_double(0x7FF0000000000000ll);
+            double lo, hi;
+            int n_cand = n_blk;      // candidate blocks: all of them, or those of the live groups
+            if (two_level) {
+                double ub = inf;
+                for (int j = sid; j < n_grp; j += scan_n) { circle(a.pblk2, j, lo, hi); ub = fmin(ub, hi); }
+                const double U2 = fmax(thr, scan_min(ub));
+                for (int j = sid; j < n_grp; j += scan_n) {
+                    circle(a.pblk2, j, lo, hi);
+                    if (lo <= U2) { const int slot = atomicAdd(&s_ngrp, 1); if (slot < NVB_PATH_GRP_MAX) s_grp[slot] = j; }
                 }
+                asm volatile("bar.sync 1, %0;" ::"r"(scan_n) : "memory");
+                if (s_ngrp > NVB_PATH_GRP_MAX) full_scan = true;
+                n_cand = s_ngrp * NVB_PATH_GROUP;
+            }
+            if (!full_scan) {
+                auto cand_block = [&](int idx) {
+                    if (!two_level) return idx;
+                    const int b1 = s_grp[idx / NVB_PATH_GROUP] * NVB_PATH_GROUP + (idx % NVB_PATH_GROUP);
+                    return b1 < n_blk ? b1 : -1;
+                };
+                double ub = inf;
+                for (int idx = sid; idx < n_cand; idx += scan_n) {
+                    const int j = cand_block(idx);
+                    if (j >= 0) { circle(a.pblk, j, lo, hi); ub = fmin(ub, hi); }
+                }
+                const double U = fmax(thr, scan_min(ub));
+                for (int idx = sid; idx < n_cand; idx += scan_n) {
+                    const int j = cand_block(idx);
+                    if (j < 0) continue;
+                    circle(a.pblk, j, lo, hi);
+                    if (lo <= U) { const int slot = atomicAdd(&s_nlive, 1); if (slot < NVB_PATH_LIVE_MAX) s_live[slot] = j; }
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(scan_n) : "memory");
+                if (s_nlive > NVB_PATH_LIVE_MAX) full_scan = true;
+            }
+            if (!full_scan) {
+                const int n_live = s_nlive;
+                for (int idx = sid; idx < n_live * NVB_PATH_BLOCK; idx += scan_n) {
+                    const int n = s_live[idx / NVB_PATH_BLOCK] * NVB_PATH_BLOCK + (idx % NVB_PATH_BLOCK);
+                    if (n < a.n_path) {
+                        const double2 pt = __ldg(path + n);
+                        const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
+                        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                        m = fmin(m, d2);
+                        if (d2 <= thr2) a.ag.coverage[(size_t)b * a.n_path + n] = 1;
+                    }
+                }
+            }
+        }
+        if (scanning && full_scan) {   // (CTA-uniform among the scanning threads)
+            for (int n = sid; n < a.n_path; n += scan_n) {
+                const double2 pt = __ldg(path + n);
+                const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
+                const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                m = fmin(m, d2);
+                if (d2 <= thr2) a.ag.coverage[(size_t)b * a.n_path + n] = 1;
             }
         }
 #pragma unroll
@@ -1119,7 +1171,7 @@ k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs
     nvb_sampler_stage_tc(sa.genc != nullptr ? sa.tc_tab : nullptr, L.tc);
     for (int k = threadIdx.x; k < a.A; k += blockDim.x) L.offs[k] = a.offsets[k];
     if (a.pblk != nullptr) {   // update_error reads the block bounds of the whole path, then a few blocks
-        const int bytes = ((a.n_path + NVB_PATH_BLOCK - 1) / NVB_PATH_BLOCK) * 32;
+        const int bytes = min(((a.n_path + NVB_PATH_BLOCK - 1) / NVB_PATH_BLOCK) * 32, 64 * 1024);
         for (int o = threadIdx.x * 128; o < bytes; o += blockDim.x * 128)
             asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(a.pblk) + o));
     } else if (a.n_path <= 4096) {
@@ -1164,6 +1216,10 @@ k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs
         if (!stepped) {
             nvb_log_idle(a, b);
             return;
+        }
+        if (a.p2p.world > 1) {   // view shards: exact differences, MIN over ranks, then fetched again
+            nvb_p2p_min_agent(a.p2p, a.exact, b, a.A, 1);
+            pre = nvb_move_preload(a, b, nullptr);
         }
     }
     const unsigned long long *s_ex = CAND ? s_exact_c : nullptr;

@@ -112,3 +112,46 @@ def test_c4_million_views(gpu):
     assert md[0] == 0 and vi[0] <= 11
     pose = synthetic.start_pose(tpath, (0.05, 3.0), 80)
     _one_agent_steps(eng, ow, pose, 2)
+
+
+@pytest.mark.parametrize("dup_at", ["far", "near"])
+def test_long_path_two_level_prefilter(gpu, dup_at):
+    """update_error over a 40 000-point path inside the agent's own CTA: two levels of bounding
+    circles prune it ("far": the filler points sit at the end of the path, away from the agents);
+    thousands of points on one spot next to the agents overflow the candidate lists and fall
+    back to the full scan ("near").  Distances, stops and coverage as the oracle's."""
+    import navsim
+    from navsim import synthetic
+    from oracle import oracle as O
+    L = synthetic.make_landscape(5003, 500, sigma=6.0)
+    kw = dict(sensor_dimensions=(40, 2), sensor_pixel_dimensions=(2, 4), step_size=5.0, n_test_angles=10,
+              n_sensor_levels=5, max_distance_to_training_path=450)
+    tpath = synthetic.training_path_for(L.shape, 5.0, 10, 0.0)
+    eng = navsim.NavEngine(L, **kw)
+    ow = O.World(L, **kw)
+    assert ow.train_from_path(tpath) == (0, -1)
+    N = 40000
+    rng = np.random.default_rng(11)
+    levels = np.array([0, 63, 127, 191, 255], np.uint8)
+    scenes = np.zeros((N, 2, 40, 3), np.uint8)
+    scenes[..., 2] = levels[rng.integers(0, 5, (N, 2, 40))]
+    scenes[:len(tpath)] = ow.scenes
+    spot = tpath[-1] if dup_at == "far" else tpath[6] + np.array([1.5, -0.5])
+    path = np.vstack([tpath, np.repeat(spot[None], N - len(tpath), axis=0)])
+    eng.set_library(scenes, path)
+    ow.set_library(scenes, path)
+    poses = synthetic.start_pose_grid(tpath, 80, n_lat=3, n_deg=3, lat=0.2, deg=8.0)
+    frames = 6
+    eng.set_agents(poses, frames)
+    eng.step(frames)
+    st = eng.state()
+    ref = ow.run_batch(poses, frames, log_best=True)
+    log = eng.log(0, frames)
+    assert np.array_equal(st["status"], ref["status"]) and np.array_equal(st["completed"], ref["completed"])
+    assert np.array_equal(st["coverage"], ref["coverage"])
+    assert np.array_equal(st["err_n"], ref["n_nav_err"]) and np.array_equal(st["err_sum"], ref["nav_err"])
+    assert np.array_equal(st["poses"], ref["poses"])
+    assert st["coverage"].sum() > 0
+    for b in range(len(poses)):
+        n = int(ref["completed"][b]) + (1 if ref["status"][b] in (1, -1) else 0)
+        assert np.array_equal(log["best_idx"][:n, b].astype(np.int32), ref["best_idx"][b, :n])
