@@ -419,6 +419,165 @@ k2_sad_hsv(DistArgs a)
     }
 }
 
+// ---- chem_weight > 0, tiled ------------------------------------------------------------------
+// The same metric on register tiles, like k2_sad_v: a CTA owns a TG x TN (glimpse x view) tile,
+// the three planes of both operands are staged per K-chunk by a cp.async ring (swizzled 16-byte
+// chunks), every thread accumulates MG x MV pairs with two sums each (X = hue/saturation part,
+// V part; nvb_hsv_word: one VCMP4, two LOP3 pairs, four VABSDIFF4 per word = 4 pixels), the
+// fixed-point score and the packed key are formed once per unit.  Work is cut into contiguous
+// unit spans per CTA exactly as in k2_sad_v.
+template <int TY, int MG, int MV, int CPR, int STAGES>
+struct HsvCfg {
+    static constexpr int TX = NVB_DIST_THREADS / TY;
+    static constexpr int TG = TY * MG;
+    static constexpr int TN = TX * MV;
+    static constexpr int KC = 16 * CPR;
+    static constexpr int PLANE_BYTES = (TG + TN) * KC;
+    static constexpr int STAGE_BYTES = 3 * PLANE_BYTES;
+    static constexpr int SMEM = STAGE_BYTES * STAGES;
+};
+
+template <int TY, int MG, int MV, int CPR, int STAGES>
+__global__ void __launch_bounds__(NVB_DIST_THREADS, 2)
+k2_sad_hsv_t(DistArgs a)
+{
+    using C = HsvCfg<TY, MG, MV, CPR, STAGES>;
+    constexpr int TX = C::TX, TG = C::TG, TN = C::TN, KC = C::KC;
+    extern __shared__ __align__(128) uint8_t smem_hsv_t[];
+    uint8_t *smem = smem_hsv_t;
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    if (a.pdl_early) nvb_grid_dep_launch();
+    const int u0 = a.spans[blockIdx.x], u1 = a.spans[blockIdx.x + 1];
+    const int nk = a.nk;
+    const int total = (u1 - u0) * nk;
+    nvb_grid_dep_wait();
+    if (a.step_counter != nullptr && blockIdx.x == 0 && tid == 0) {
+        *a.step_counter += 1;
+        a.tie_count[0] = 0;
+        a.tie_count[1] = 0;
+        if (a.epoch != nullptr) *a.epoch += 1;
+    }
+    if (total <= 0) return;
+
+    int l_gt = u0 / a.n_vt, l_vt = u0 - l_gt * a.n_vt, l_kc = 0, l_it = 0;
+    auto load_next = [&]() {
+        uint8_t *st = smem + (l_it % STAGES) * C::STAGE_BYTES;
+        const int kbyte = l_kc * KC;
+        for (int q = tid; q < 3 * (TG + TN) * CPR; q += NVB_DIST_THREADS) {
+            const int pl = q / ((TG + TN) * CPR), qq = q - pl * (TG + TN) * CPR;
+            const int row = qq / CPR, c = qq - row * CPR;
+            const uint8_t *src;
+            int ok;
+            if (row < TG) {
+                const int g = l_gt * TG + row;
+                ok = (g < a.G) && (kbyte + 16 * c < a.Ppad);
+                const uint8_t *base = (pl == 0) ? a.gh : (pl == 1) ? a.gs : a.gv;
+                src = base + (size_t)(ok ? g : 0) * a.Ppad + (ok ? kbyte + 16 * c : 0);
+            } else {
+                const int v = l_vt * TN + (row - TG);
+                ok = (v < a.N) && (kbyte + 16 * c < a.Ppad);
+                const uint8_t *base = (pl == 0) ? a.lh : (pl == 1) ? a.ls : a.lv;
+                src = base + (size_t)(ok ? v : 0) * a.Ppad + (ok ? kbyte + 16 * c : 0);
+            }
+            const int r = (row < TG) ? row : row - TG;
+            uint8_t *dst = st + pl * C::PLANE_BYTES + (row < TG ? 0 : TG * KC) + r * KC + 16 * (c ^ nvb_swz<CPR>(r));
+            nvb_cp_async16(dst, src, ok ? 16 : 0);
+        }
+        l_it++;
+        if (++l_kc == nk) {
+            l_kc = 0;
+            if (++l_vt == a.n_vt) { l_vt = 0; l_gt++; }
+        }
+    };
+
+    uint32_t xs[MG][MV], vs[MG][MV];
+#pragma unroll
+    for (int i = 0; i < MG; i++)
+#pragma unroll
+        for (int j = 0; j < MV; j++) { xs[i][j] = 0; vs[i][j] = 0; }
+    unsigned long long best[MG];
+#pragma unroll
+    for (int i = 0; i < MG; i++) best[i] = NVB_KEY_NONE;
+
+    int goff[MG], gsw[MG], voff[MV], vsw[MV];
+#pragma unroll
+    for (int i = 0; i < MG; i++) { int r = ty + TY * i; goff[i] = r * KC; gsw[i] = nvb_swz<CPR>(r) << 4; }
+#pragma unroll
+    for (int j = 0; j < MV; j++) { int r = tx + TX * j; voff[j] = TG * KC + r * KC; vsw[j] = nvb_swz<CPR>(r) << 4; }
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < total) load_next();
+        nvb_cp_async_commit();
+    }
+    constexpr int RW = (TX < 32) ? TX : 32;
+    int gt = u0 / a.n_vt, vt = u0 - gt * a.n_vt, kc = 0;
+    for (int it = 0; it < total; it++) {
+        nvb_cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (l_it < total) load_next();
+        nvb_cp_async_commit();
+        const uint8_t *st = smem + (it % STAGES) * C::STAGE_BYTES;
+        for (int c = 0; c < CPR; c++) {
+            uint4 qh[MG], qs[MG], qv[MG];
+#pragma unroll
+            for (int i = 0; i < MG; i++) {
+                const int o = goff[i] + ((c << 4) ^ gsw[i]);
+                qh[i] = *reinterpret_cast<const uint4 *>(st + o);
+                qs[i] = *reinterpret_cast<const uint4 *>(st + C::PLANE_BYTES + o);
+                qv[i] = *reinterpret_cast<const uint4 *>(st + 2 * C::PLANE_BYTES + o);
+            }
+#pragma unroll
+            for (int j = 0; j < MV; j++) {
+                const int o = voff[j] + ((c << 4) ^ vsw[j]);
+                const uint4 fh = *reinterpret_cast<const uint4 *>(st + o);
+                const uint4 fs = *reinterpret_cast<const uint4 *>(st + C::PLANE_BYTES + o);
+                const uint4 fv = *reinterpret_cast<const uint4 *>(st + 2 * C::PLANE_BYTES + o);
+#pragma unroll
+                for (int i = 0; i < MG; i++) {
+                    nvb_hsv_word(qh[i].x, qs[i].x, qv[i].x, fh.x, fs.x, fv.x, xs[i][j], vs[i][j]);
+                    nvb_hsv_word(qh[i].y, qs[i].y, qv[i].y, fh.y, fs.y, fv.y, xs[i][j], vs[i][j]);
+                    nvb_hsv_word(qh[i].z, qs[i].z, qv[i].z, fh.z, fs.z, fv.z, xs[i][j], vs[i][j]);
+                    nvb_hsv_word(qh[i].w, qs[i].w, qv[i].w, fh.w, fs.w, fv.w, xs[i][j], vs[i][j]);
+                }
+            }
+        }
+        if (++kc == nk) {
+            kc = 0;
+            const int nvalid = a.N - vt * TN;
+#pragma unroll
+            for (int i = 0; i < MG; i++)
+#pragma unroll
+                for (int j = 0; j < MV; j++) {
+                    const int vloc = tx + TX * j;
+                    if (vloc < nvalid) {
+                        const unsigned long long key = (nvb_hsv_score(xs[i][j], vs[i][j], a.cw) << a.idx_bits) |
+                                                       (unsigned long long)(a.view_offset + (long long)vt * TN + vloc);
+                        best[i] = key < best[i] ? key : best[i];
+                    }
+                    xs[i][j] = 0;
+                    vs[i][j] = 0;
+                }
+            if (it == total - 1 || vt == a.n_vt - 1) {
+#pragma unroll
+                for (int i = 0; i < MG; i++) {
+                    unsigned long long key = best[i];
+#pragma unroll
+                    for (int o = RW / 2; o > 0; o >>= 1) {
+                        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+                        key = other < key ? other : key;
+                    }
+                    const int g = gt * TG + ty + TY * i;
+                    if ((tx % RW) == 0 && g < a.G && key != NVB_KEY_NONE) atomicMin(a.keys + g, key);
+                    best[i] = NVB_KEY_NONE;
+                }
+            }
+            if (++vt == a.n_vt) { vt = 0; gt++; }
+        }
+    }
+}
+
 // ---- exact FP64 difference of one (glimpse, view) pair -----------------------
 // The literal operation sequence of util.pyx:48-72 (no FMA contraction), so
 // that fam = H*W - diff is bit-identical to the reference.  q*/f* are rows of

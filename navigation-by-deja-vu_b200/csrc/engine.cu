@@ -962,6 +962,35 @@ static int launch_distance_tc(nvb_engine *e, int G, bool bump_step, bool encode_
     return launch_tc_cfg<64, 8, false>(e, ta);
 }
 
+// chem_weight > 0 on register tiles (16 glimpses x 128 views per CTA, 2 x 4 pairs per thread)
+template <int CPR>
+static int launch_hsv_tiled(nvb_engine *e, DistArgs da)
+{
+    constexpr int TY = 8, MG = 2, MV = 4, STAGES = 3;
+    using C = HsvCfg<TY, MG, MV, CPR, STAGES>;
+    auto kern = k2_sad_hsv_t<TY, MG, MV, CPR, STAGES>;
+    static int occ_dev[64] = {0};
+    int &occ = occ_dev[e->device & 63];
+    if (occ == 0) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NVB_DIST_THREADS, C::SMEM));
+        if (occ < 1) occ = 1;
+    }
+    const int n_gt = (da.G + C::TG - 1) / C::TG, n_vt = (da.N + C::TN - 1) / C::TN;
+    const long long units = (long long)n_gt * n_vt;
+    long long n_cta = (long long)e->sm_count * occ;
+    if (n_cta > units) n_cta = units;
+    int rc = build_spans(e, n_gt, n_vt, (int)n_cta);
+    if (rc) return rc;
+    da.n_vt = n_vt;
+    da.vt_per_split = 0;
+    da.spans = e->d_spans;
+    CK(launch_seq(kern, dim3((unsigned)n_cta), dim3(NVB_DIST_THREADS), (size_t)C::SMEM, e->stream, da));
+    e->launches++;
+    CK(cudaGetLastError());
+    return NVB_OK;
+}
+
 // K2 over glimpses [0, G) of the engine's glimpse buffers; keys must be reset.
 // glimpses_encoded: the sampler of the stepping loop wrote the thermometer planes as well.
 static int launch_distance(nvb_engine *e, int G, bool bump_step = false, bool glimpses_encoded = false)
@@ -987,6 +1016,19 @@ static int launch_distance(nvb_engine *e, int G, bool bump_step = false, bool gl
     da.idx_bits = (e->cw == 0.0) ? 32 : 28;
     da.pdl_early = (bump_step && early_trigger()) ? 1 : 0;
     da.tl = bump_step ? e->d_tl : nullptr;
+    static const bool hsv_untiled = getenv("NAVSIM_B200_HSV_UNTILED") != nullptr;
+    if (e->cw != 0.0 && G >= 16 && !hsv_untiled) {
+        switch (e->cpr) {
+        case 1: return launch_hsv_tiled<1>(e, da);
+        case 2: return launch_hsv_tiled<2>(e, da);
+        case 3: return launch_hsv_tiled<3>(e, da);
+        case 4: return launch_hsv_tiled<4>(e, da);
+        case 5: return launch_hsv_tiled<5>(e, da);
+        case 7: return launch_hsv_tiled<7>(e, da);
+        case 8: return launch_hsv_tiled<8>(e, da);
+        }
+        return fail(NVB_E_INVALID, "unsupported chunk count %d", e->cpr);
+    }
     if (e->cw != 0.0) {
         const size_t smem = (size_t)3 * NVB_HSV_TG * e->Ppad;
         static size_t attr_set[64] = {0};

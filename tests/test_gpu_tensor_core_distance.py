@@ -104,3 +104,36 @@ def test_trajectories_identical_with_either_kernel(gpu, name):
     assert np.array_equal(la["afam"], lb["afam"], equal_nan=True)
     for k in ("status", "completed", "coverage", "err_n", "err_sum"):
         assert np.array_equal(sa[k], sb[k])
+
+
+@pytest.mark.parametrize("cw", [0.3, 1.0, 0.123])
+@pytest.mark.parametrize("W,H,G,N", [(40, 2, 300, 1414), (20, 4, 17, 130), (8, 2, 1000, 255), (50, 5, 64, 700), (64, 64, 40, 150)])
+def test_chemistry_kernel_min_argmin(gpu, cw, W, H, G, N):
+    """chem_weight > 0 (tiled k2_sad_hsv_t for 16 glimpses and more): the fixed-point score
+    floor(4096 * (cw * 0.5 * X + (1 - cw) * V)) of the oracle's integer sums, minimum and lowest
+    view index, exact."""
+    import navsim
+    from oracle import oracle as O
+    rng = np.random.default_rng(int(cw * 1000) + W * 7 + G)
+    L = np.zeros((64, 64, 3), np.uint8)
+    eng = navsim.NavEngine(L, (W, H), 1.0, n_test_angles=4, sensor_pixel_dimensions=(2, 2), chem_weight=cw)
+    levels = np.array([0, 63, 127, 191, 255], np.uint8)
+    scenes = np.zeros((N, H, W, 3), np.uint8)
+    scenes[..., 0] = rng.integers(0, 3, (N, H, W)) * 85
+    scenes[..., 1] = rng.integers(0, 2, (N, H, W)) * 127
+    scenes[..., 2] = levels[rng.integers(0, 5, (N, H, W))]
+    scenes[N // 2] = scenes[3]
+    scenes[N - 1] = scenes[3]
+    eng.set_library(scenes)
+    q = scenes[rng.integers(0, N, G)].copy()
+    flip = rng.random((G, H, W)) < 0.3
+    q[..., 2][flip] = levels[rng.integers(0, 5, int(flip.sum()))]
+    q[..., 0][flip] = rng.integers(0, 3, int(flip.sum())) * 85
+    q[0] = scenes[3]
+    md, vi = eng.familiarity_min(q)
+    for g in rng.choice(G, size=min(G, 16), replace=False):
+        xt, vt = O.sad_int(scenes, q[g])
+        score = np.floor(4096.0 * ((xt.astype(np.float64) * 0.5) * cw + (1.0 - cw) * vt.astype(np.float64)))
+        assert md[g] == score.min() / 4096.0, (g, md[g], score.min() / 4096.0)
+        assert vi[g] == int(np.argmin(score))
+    assert md[0] == 0 and vi[0] == 3
