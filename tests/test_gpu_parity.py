@@ -324,3 +324,43 @@ def test_host_driven_step_io_matches_oracle(mods, name, buffers):
         assert np.allclose(fam[:n, b], r["afam"][:n].max(axis=1), rtol=FAM_RTOL, atol=0)
     st = eng.state()
     assert eng.steps_done == K
+
+
+FAM_RTOL_CHEM = 1e-6   # angle_familiarity with chem_weight > 0, see below (north_star: FP32-level)
+
+
+@pytest.mark.parametrize("cw", [0.123, 0.3, 0.77])
+def test_non_dyadic_chem_weight(mods, cw):
+    """chem_weight > 0: the distance kernel ranks views by floor(4096 * f) and a heading that
+    is NOT tied with another heading takes its exact FP64 value from the lowest-index view at
+    that minimum; another view in the same 1/4096 bucket can be lower by up to 1/(4096 * 255),
+    so angle_familiarity of such headings is exact only to ~1e-8 relative (asserted: 1e-6;
+    most values are bit-exact).  Headings tied within the band are resolved over every view in
+    exact FP64, so heading sequences, positions, stops and coverage are exact all the same."""
+    navsim, util, O = mods
+    L, w, tpath, pose, frames = build_case("chem")
+    w = dict(w)
+    w["chem_weight"] = cw
+    frames = min(frames, 100)
+    eng = navsim.NavEngine(L, **w)
+    ow = O.World(L, **w)
+    assert eng.train_from_path(tpath) == (0, -1) and ow.train_from_path(tpath) == (0, -1)
+    poses = np.vstack([np.asarray(pose)[None], agent_grid(tpath, w)])
+    eng.set_agents(poses, frames)
+    eng.step(frames, log_afam=True)
+    log = eng.log(0, frames, afam=True)
+    st = eng.state()
+    n_exact = n_vals = 0
+    for b, p in enumerate(poses):
+        ag = ow.new_agent(*p)
+        r = ow.run(ag, frames, log_afam=True)
+        n = r["completed"] + (1 if r["status"] in (1, -1) else 0)
+        assert st["status"][b] == r["status"] and st["completed"][b] == r["completed"]
+        assert np.array_equal(log["best_idx"][:n, b], r["best_idx"][:n]), (cw, b)
+        assert np.array_equal(log["poses"][:n, b], r["pos"][:n])
+        assert np.allclose(log["afam"][:n, b], r["afam"][:n], rtol=FAM_RTOL_CHEM, atol=0)
+        assert np.array_equal(log["step_fam"][:n, b], r["afam"][:n].max(axis=1))     # the winner is exact
+        assert np.array_equal(st["coverage"][b], ag._cov)
+        n_exact += int(np.sum(log["afam"][:n, b] == r["afam"][:n]))
+        n_vals += n * r["afam"].shape[1]
+    assert n_exact > 0.9 * n_vals
