@@ -2,7 +2,7 @@
 # One GPU-box pass that regenerates everything under profiles/ for a round:
 #   tools/evidence_run.sh r01        (run through gpurun; results land in gpurun_out/)
 # Order matters: every ncu pass repeats a command that has already exited 0 without ncu.
-tag=${1:-r01}
+tag=${1:-r02}
 out=gpurun_out
 mkdir -p $out
 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"
@@ -16,10 +16,10 @@ if [ $rc -eq 0 ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \
       --log-file $out/${tag}_launches.csv python bench.py --steps 20 --warmup 3 --quick --no-cpu > $out/${tag}_ncu1.log 2>&1
   echo "ncu launches rc=$?"
-  ncu --set full --clock-control none --import-source on -k regex:k2_sad_v -s 110 -c 2 -f \
+  ncu --set full --clock-control none --import-source on -k regex:k2_ -s 40 -c 2 -f \
       -o $out/${tag}_k2 python bench.py --steps 20 --warmup 3 --quick --no-cpu > $out/${tag}_ncu2.log 2>&1
   echo "ncu k2 rc=$?"
-  ncu --set full --clock-control none --import-source on -k regex:k3_ -s 330 -c 3 -f \
+  ncu --set full --clock-control none --import-source on -k regex:k3_ -s 120 -c 3 -f \
       -o $out/${tag}_k3 python bench.py --steps 20 --warmup 3 --quick --no-cpu > $out/${tag}_ncu3.log 2>&1
   echo "ncu k3 rc=$?"
 fi
