@@ -265,20 +265,27 @@ def run_ours(args):
     step_io = eng.bind_step_io(a_in, a_best, a_pose, a_fam)   # same pinned buffers every call
     a_in[:] = poses
     eng.set_agents(poses)
-    for _ in range(W):
+    # warm-up: W calls, and one full rewind period so that the step log has its final capacity
+    # (it doubles as a run grows; a doubling re-captures the step graph) before anything is timed
+    for _ in range(max(W, rewind_every + 1)):
         step_io()
         a_in[:] = a_pose
-    eng.set_agents(poses)
+    eng.rewind()
     a_in[:] = poses
     barrier()
     t0 = time.perf_counter()
+    per_call = []
     for i in range(1 if args.quick else K):
         if i and i % rewind_every == 0:
             eng.rewind()
             a_in[:] = poses
+        tc0 = time.perf_counter()
         step_io()                     # H2D poses, one step-batch, D2H results, one synchronisation
+        per_call.append(time.perf_counter() - tc0)
         a_in[:] = a_pose              # the caller feeds the new poses back in, like a host-driven loop
     torch.cuda.synchronize()
+    if os.environ.get("NAVSIM_BENCH_DEBUG"):
+        print("e2e per call us:", [round(x * 1e6) for x in per_call], file=sys.stderr)
     t_e2e = max_over_ranks(time.perf_counter() - t0) * (K if args.quick else 1)
     e2e_result_checksum = float(np.nansum(h_fam.numpy()))
     barrier()

@@ -219,7 +219,9 @@ int nvb_debug_step_clocks(nvb_engine *e, long long *out);
 /* Tuning aid: `nsteps` step-batches as nvb_agents_step runs them, every CTA of the four
  * step kernels (distance, decide, ties, move+sample) stamping the global timer when it
  * becomes resident, when its grid dependency is met and when it is done.
- * out [4][2048][3], ns, of the last step-batch; 0 = CTA not present. */
+ * out [6][2048][3], ns, of the last step-batch; 0 = CTA not present.  Slots 4 and 5 hold
+ * per-CTA checkpoints of the single-launch step kernel (k3_step_tm): inputs in, pose known,
+ * update_error done | all warps at the gather, window landed, -. */
 int nvb_debug_timeline(nvb_engine *e, int nsteps, long long *out);
 
 /* ---- landscape preparation on the device ------------------------------------------------

@@ -34,6 +34,7 @@
 #define NVB_TC_THREADS 192
 #define NVB_TC_TM 128          /* glimpse rows per tile (UMMA M) */
 #define NVB_TC_MAX_PLANES 8
+#define NVB_TC_NT 256          /* views per tile (UMMA N) */
 
 struct TcPlanes {
     int n_planes;                          // thermometer planes (after splitting heavy weights)
@@ -53,8 +54,9 @@ struct TcArgs {
     int sad_const;               // C = P * sum of plane weights
     int *step_counter;           // resident loop: bumped once per launch, else nullptr
     int *tie_count;
-    int2 *cand;                  // TOP2 kernels: [G][n_vt] the two smallest tile-local keys (-256 * dot + column) per
-                                 // glimpse and view tile (0x7FFFFFFF = none), for the candidate-based decide
+    int2 *tmin;                  // TILEMIN kernels: [G][n_vt] the two smallest tile-local keys (-256 * dot + column;
+                                 // 0x7FFFFFFF = none) of every glimpse and view tile, for the single-launch step
+                                 // (step_tm.cuh, k3_step_tm); the packed keys are then not written at all
     unsigned long long *epoch;   // view shards over NVLink: launches so far (step.cuh), else nullptr
     int pdl_early;
     long long *tl;
@@ -178,34 +180,80 @@ __device__ __forceinline__ int nvb_tc_fold(uint32_t taddr, int c0, int nvalid, i
     return best;
 }
 
-// The same keeping the TWO smallest keys of the row (best <= second): the step kernel that
-// follows resolves headings tied at the integer minimum from these candidates instead of
-// rescanning the library (step.cuh, nvb_decide_cand).  Second smallest of {best, second, lo, hi}
-// with best <= second, lo <= hi is min3(max(best, lo), second, hi).
-template <int W>
-__device__ __forceinline__ void nvb_tc_fold2(uint32_t taddr, int c0, int nvalid, int &best, int &second)
+// 32 lanes x 64 consecutive columns
+__device__ __forceinline__ void nvb_tmem_ld64(uint32_t taddr, uint32_t (&r)[64])
 {
-    uint32_t r[W];
-    if (W == 32) nvb_tmem_ld32(taddr + (uint32_t)c0, reinterpret_cast<uint32_t (&)[32]>(r));
-    else nvb_tmem_ld16(taddr + (uint32_t)c0, reinterpret_cast<uint32_t (&)[16]>(r));
-    nvb_tmem_wait_ld();
-    if (c0 + W <= nvalid) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr)
+        : "memory");
+}
+
+// minimum of -256 * dot + column over 64 accumulator columns [c0, c0 + 64) already in registers.
+// TOP2: also the second smallest key (best <= second): the step kernel resolves headings tied
+// at the integer minimum from these two instead of rescanning the tile (step_tm.cuh).  Second
+// smallest of {best, second, lo, hi} with best <= second, lo <= hi is min3(max(best, lo), second, hi).
+template <bool TOP2>
+__device__ __forceinline__ void nvb_tc_min64(const uint32_t (&r)[64], int c0, int nvalid, int &best, int &second)
+{
+#if defined(NVB_TC_EXP_NO_FOLD)   /* tools/micro experiments only */
+    best ^= (int)r[0] ^ (int)r[63];
+    return;
+#endif
+    if (c0 + 64 <= nvalid) {
 #pragma unroll
-        for (int j = 0; j + 1 < W; j += 2) {
+        for (int j = 0; j < 64; j += 2) {
             const int k1 = (int)r[j] * -256 + (c0 + j), k2 = (int)r[j + 1] * -256 + (c0 + j + 1);
-            const int lo = min(k1, k2), hi = max(k1, k2);
-            second = __vimin3_s32(max(best, lo), second, hi);
-            best = min(best, lo);
+            if (TOP2) {
+                const int lo = min(k1, k2), hi = max(k1, k2);
+                second = __vimin3_s32(max(best, lo), second, hi);
+                best = min(best, lo);
+            } else {
+                best = __vimin3_s32(best, k1, k2);
+            }
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < W; j++)
+        for (int j = 0; j < 64; j++)
             if (c0 + j < nvalid) {
                 const int k1 = (int)r[j] * -256 + (c0 + j);
-                second = min(second, max(best, k1));
+                if (TOP2) second = min(second, max(best, k1));
                 best = min(best, k1);
             }
     }
+}
+
+// One finished 128 x 256 accumulator (this thread's row): the row's minimum of -256 * dot +
+// column.  The TMEM loads are software-pipelined -- 64 columns are folded while the next 64 are
+// in flight (a load waited for right after its issue exposes the whole TMEM latency, eight
+// times per item: measured 1.6 us per item against 0.7 us of MMA) -- and `release` runs as soon
+// as the last load has landed, before the last fold, so the MMA warp gets the buffer back early.
+template <bool TOP2, typename Release>
+__device__ __forceinline__ int2 nvb_tc_fold_item(uint32_t taddr, int nvalid, Release release)
+{
+    static_assert(NVB_TC_NT == 256, "four chunks of 64 columns");
+    uint32_t ra[64], rb[64];
+    int best = 0x7FFFFFFF, second = 0x7FFFFFFF;
+#if defined(NVB_TC_EXP_NO_EPI_LD)   /* tools/micro experiments only */
+    release();
+    return make_int2((int)taddr, 0);
+#endif
+    nvb_tmem_ld64(taddr, ra);
+    nvb_tmem_wait_ld();
+    nvb_tmem_ld64(taddr + 64u, rb);
+    nvb_tc_min64<TOP2>(ra, 0, nvalid, best, second);
+    nvb_tmem_wait_ld();
+    nvb_tmem_ld64(taddr + 128u, ra);
+    nvb_tc_min64<TOP2>(rb, 64, nvalid, best, second);
+    nvb_tmem_wait_ld();
+    nvb_tmem_ld64(taddr + 192u, rb);
+    nvb_tc_min64<TOP2>(ra, 128, nvalid, best, second);
+    nvb_tmem_wait_ld();
+    release();
+    nvb_tc_min64<TOP2>(rb, 192, nvalid, best, second);
+    return make_int2(best, second);
 }
 
 template <int KCH, int NT, int STAGES>
@@ -235,7 +283,7 @@ __device__ __forceinline__ void nvb_tc_next(const TcArgs &a, int &gt, int &vt)
     else { if (++vt == a.n_vt) { vt = 0; gt++; } }
 }
 
-template <int KCH, int NT, int STAGES, bool TOP2 = false>
+template <int KCH, int NT, int STAGES, bool TILEMIN = false>
 __global__ void __launch_bounds__(NVB_TC_THREADS, 1)
 k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, TcArgs a)
 {
@@ -345,24 +393,29 @@ k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensor
             nvb_tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256);
             const int nvalid = min(NT, a.N - vt * NT);
-            int best = 0x7FFFFFFF;   // min over columns of -256 * dot + column
-            int second = 0x7FFFFFFF;
+            int best, second = 0x7FFFFFFF;   // min over columns of -256 * dot + column (and the runner-up)
+            if (NT == 256) {
+                const int2 b2 = nvb_tc_fold_item<TILEMIN>(taddr, nvalid, [&]() {
+                    nvb_tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) nvb_mbar_arrive(tempty + buf);
+                });
+                best = b2.x; second = b2.y;
+            } else {
+                best = 0x7FFFFFFF;
 #pragma unroll
-            for (int c0 = 0; c0 < NT; c0 += 32) {
-                if (TOP2) {
-                    if (NT - c0 >= 32) nvb_tc_fold2<32>(taddr, c0, nvalid, best, second);
-                    else nvb_tc_fold2<16>(taddr, c0, nvalid, best, second);
-                } else {
+                for (int c0 = 0; c0 < NT; c0 += 32) {
                     if (NT - c0 >= 32) best = nvb_tc_fold<32>(taddr, c0, nvalid, best);
                     else best = nvb_tc_fold<16>(taddr, c0, nvalid, best);
                 }
+                nvb_tc_fence_before();
+                __syncwarp();
+                if (lane == 0) nvb_mbar_arrive(tempty + buf);
             }
-            nvb_tc_fence_before();
-            __syncwarp();
-            if (lane == 0) nvb_mbar_arrive(tempty + buf);
             const int g = gt * C::TM + row;
-            if (TOP2 && g < a.G) a.cand[(size_t)g * a.n_vt + vt] = make_int2(best, second);
-            if (g < a.G && best != 0x7FFFFFFF) {
+            if (TILEMIN) {
+                if (g < a.G) a.tmin[(size_t)g * a.n_vt + vt] = make_int2(best, second);
+            } else if (g < a.G && best != 0x7FFFFFFF) {
                 const int col = best & 255;
                 const int dot = -(best >> 8);
                 const unsigned long long sad = (unsigned long long)((a.sad_const - dot) >> 1);
@@ -370,6 +423,224 @@ k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensor
                 atomicMin(a.keys + g, (sad << 32) | v);
             }
             nvb_tc_next(a, gt, vt);
+        }
+    }
+    nvb_tc_fence_before();
+    __syncthreads();
+    if (warp == 2) nvb_tmem_dealloc(tmem_base, 512);
+    nvb_tl_stamp(a.tl, 0, 2);
+}
+
+// ---- view-tile-stationary variant ----------------------------------------------------------
+// Sensors of few pixels (the reference's default 40 x 2 sensor at 5 levels: K = 320 bytes per
+// row) leave the streaming kernel above bound by its own bookkeeping, not by the tensor pipe.
+// Measured with in-kernel cycle stamps (tools/micro/tc_sad.cu, NVB_TC_EXP_STAMPS): the thread
+// that issues the MMAs spends ~450 cycles in every tcgen05.commit, and a kernel that releases
+// each K-chunk stage with its own commit pays that five or six times per 128 x 256 item --
+// 3200 cycles per item against 1340 cycles of MMA.  Here:
+//   * the VIEW tile (256 rows x all K) stays resident in shared memory while the CTA walks the
+//     glimpse tiles of its span (items are ordered view-tile-major): an item only loads its 128
+//     glimpse rows, and a view tile of a 10^6-view library comes from HBM exactly once;
+//   * the glimpse rows of an item land as ONE group of K-chunks on one barrier, the MMA thread
+//     issues the whole item and commits ONCE (accumulator complete); the epilogue, woken by
+//     that commit, hands the glimpse slot back to the producer with a plain mbarrier arrive;
+//   * TWO warps issue MMAs, one the even items of the span (accumulator buffer 0), one the odd
+//     items (buffer 1): while one sits out its commit the other keeps the tensor pipe fed
+//     (one issuer alone: 1840 cycles per item, 1340 of them MMA).
+// K is cut into KCH-byte chunks (64: 64-byte swizzle, no padding beyond a multiple of 64).
+// Shared memory: kchunks x NT x KCH (view tile) + a_slots x kchunks x TM x KCH (glimpse ring).
+#define NVB_TCBS_KCH 64
+#define NVB_TCBS_MAX_SLOTS 4
+#define NVB_TCBS_THREADS 224   /* producer, MMA issuer (even items), 4 epilogue warps, MMA issuer (odd items) */
+
+__host__ __device__ inline int nvb_tcbs_smem(int kchunks, int a_slots, int kch = NVB_TCBS_KCH)
+{
+    return kchunks * NVB_TC_NT * kch + a_slots * kchunks * NVB_TC_TM * kch + 1024 /* alignment slack */ + 256 /* barriers */;
+}
+// glimpse slots that fit beside the view tile (at least 2 for the kernel to apply)
+__host__ __device__ inline int nvb_tcbs_slots(int kchunks, int kch = NVB_TCBS_KCH)
+{
+    const int s = (200 * 1024 - kchunks * NVB_TC_NT * kch) / (kchunks * NVB_TC_TM * kch);
+    return s > NVB_TCBS_MAX_SLOTS ? NVB_TCBS_MAX_SLOTS : s;
+}
+
+template <bool TILEMIN, int KCH = NVB_TCBS_KCH>
+__global__ void __launch_bounds__(NVB_TCBS_THREADS, 1)
+k2_tc_bs(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, TcArgs a, int a_slots)
+{
+    constexpr int NT = NVB_TC_NT, TM = NVB_TC_TM;
+    constexpr int A_BYTES = TM * KCH, B_BYTES = NT * KCH;
+    extern __shared__ uint8_t smem_tc_raw[];
+    uint8_t *smem = smem_tc_raw + ((1024u - (nvb_smem_u32(smem_tc_raw) & 1023u)) & 1023u);
+    uint8_t *smem_b = smem;                                   // [kchunks][NT][KCH]
+    uint8_t *smem_a = smem + (size_t)a.kchunks * B_BYTES;     // [a_slots][kchunks][TM][KCH]
+    const size_t slot_bytes = (size_t)a.kchunks * A_BYTES;
+    uint64_t *afull = reinterpret_cast<uint64_t *>(smem_a + (size_t)a_slots * slot_bytes);
+    uint64_t *aempty = afull + NVB_TCBS_MAX_SLOTS;
+    uint64_t *bfull = aempty + NVB_TCBS_MAX_SLOTS;   // view tile landed
+    uint64_t *bempty = bfull + 1;                    // every MMA that reads the view tile has completed
+    uint64_t *tfull = bempty + 1;                    // accumulator buffer ready for the epilogue
+    uint64_t *tempty = tfull + 2;                    // accumulator buffer drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    nvb_tl_stamp(a.tl, 0, 0);
+    if (a.pdl_early) nvb_grid_dep_launch();
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < a_slots; s++) {
+            nvb_mbar_init(afull + s, 1);
+            nvb_mbar_init(aempty + s, 1);
+        }
+        nvb_mbar_init(bfull, 1);
+        nvb_mbar_init(bempty, 3);   // both issuers have seen the tile + the epilogue has seen its last item complete
+        nvb_mbar_init(tfull + 0, 1); nvb_mbar_init(tfull + 1, 1);
+        nvb_mbar_init(tempty + 0, 4); nvb_mbar_init(tempty + 1, 4);
+        nvb_fence_barrier_init();
+        nvb_prefetch_tmap(&tm_a);
+        nvb_prefetch_tmap(&tm_b);
+    }
+    if (warp == 2) nvb_tmem_alloc(tmem_slot, 512);
+    nvb_tc_fence_before();
+    __syncthreads();
+    nvb_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int u0 = a.spans[blockIdx.x], u1 = a.spans[blockIdx.x + 1];
+
+    if (warp == 0) {
+        // ---- TMA producer.  The library is not written by any kernel of the step sequence: the
+        // first view tile is requested before the dependency wait, the glimpse rows after it.
+        int s = 0;
+        uint32_t ph = 0, bph = 0;
+        int cur_vt = -1;
+        bool waited = false;
+        for (int u = u0; u < u1; u++) {
+            const int vt = u / a.n_gt, gt = u - vt * a.n_gt;
+            if (lane == 0 && vt != cur_vt) {
+                if (cur_vt >= 0) { nvb_mbar_wait(bempty, bph); bph ^= 1u; }
+                nvb_mbar_expect_tx(bfull, (uint32_t)(a.kchunks * B_BYTES));
+                for (int kc = 0; kc < a.kchunks; kc++)
+                    nvb_tma_load_2d(smem_b + (size_t)kc * B_BYTES, &tm_b, kc * KCH, vt * NT, bfull);
+            }
+            cur_vt = vt;
+            if (!waited) {
+                nvb_grid_dep_wait();   // the glimpses are written by the previous kernel of the step sequence
+                nvb_tl_stamp(a.tl, 0, 1);
+                waited = true;
+            }
+            if (lane == 0) {
+                nvb_mbar_wait(aempty + s, ph ^ 1u);
+                nvb_mbar_expect_tx(afull + s, (uint32_t)slot_bytes);
+                for (int kc = 0; kc < a.kchunks; kc++)
+                    nvb_tma_load_2d(smem_a + (size_t)s * slot_bytes + (size_t)kc * A_BYTES, &tm_a, kc * KCH, gt * TM, afull + s);
+            }
+            __syncwarp();
+            if (++s == a_slots) { s = 0; ph ^= 1u; }
+        }
+        if (!waited) nvb_grid_dep_wait();
+    } else {
+        nvb_grid_dep_wait();
+    }
+    if (a.step_counter != nullptr && blockIdx.x == 0 && tid == 32) {
+        *a.step_counter += 1;
+        a.tie_count[0] = 0;
+        a.tie_count[1] = 0;
+        if (a.epoch != nullptr) *a.epoch += 1;
+    }
+
+    if (warp == 1 || warp == 6) {
+        // ---- MMA issuers: warp 1 the even items of the span, warp 6 the odd ones.  Per item one
+        // wait for its inputs, all its MMAs, one commit.  Both walk every item to keep track of
+        // the view tile: each acknowledges a tile once it has seen it land (third of the three
+        // arrivals that let the producer replace it is the epilogue's, after the tile's last
+        // item), so neither can fall a barrier phase behind.
+        constexpr uint32_t idesc = nvb_umma_idesc_i8(TM, NT);
+        const int mine = (warp == 1) ? 0 : 1;
+        uint32_t bph = 0;
+        int cur_vt = -1;
+        for (int u = u0; u < u1; u++) {
+            const int it = u - u0;
+            const int vt = u / a.n_gt;
+            if (lane == 0 && vt != cur_vt) {
+                nvb_mbar_wait(bfull, bph);
+                bph ^= 1u;
+                if (vt != (u1 - 1) / a.n_gt) nvb_mbar_arrive(bempty);   // (the last tile of the span is never replaced)
+            }
+            cur_vt = vt;
+            if ((it & 1) != mine) continue;
+            const int buf = mine, s = it % a_slots;
+            const uint32_t tph = (uint32_t)(it >> 1) & 1u, ph = (uint32_t)(it / a_slots) & 1u;
+            if (lane == 0) {
+                nvb_mbar_wait(tempty + buf, tph ^ 1u);   // the epilogue has drained this buffer
+                nvb_mbar_wait(afull + s, ph);
+                nvb_tc_fence_after();
+#if defined(NVB_TC_EXP_STAMPS)   /* tools/micro experiments only */
+                if (a.tl != nullptr && blockIdx.x == 0 && it < 60) a.tl[20000 + it * 8 + 0] = clock64();
+#endif
+                const uint8_t *slot = smem_a + (size_t)s * slot_bytes;
+                for (int kc = 0; kc < a.kchunks; kc++) {
+                    const uint64_t da = nvb_umma_desc<KCH>(slot + (size_t)kc * A_BYTES);
+                    const uint64_t db = nvb_umma_desc<KCH>(smem_b + (size_t)kc * B_BYTES);
+#pragma unroll
+                    for (int j = 0; j < KCH / 32; j++)   // 32 bytes of K per instruction: +2 in 16-byte units
+                        nvb_umma_i8(tmem_base + (uint32_t)(buf * 256), da + (uint64_t)(2 * j), db + (uint64_t)(2 * j),
+                                    idesc, (uint32_t)((kc | j) != 0));
+                }
+#if defined(NVB_TC_EXP_STAMPS)
+                if (a.tl != nullptr && blockIdx.x == 0 && it < 60) a.tl[20000 + it * 8 + 1] = clock64();
+#endif
+                nvb_umma_commit(tfull + buf);   // accumulator complete
+#if defined(NVB_TC_EXP_STAMPS)
+                if (a.tl != nullptr && blockIdx.x == 0 && it < 60) a.tl[20000 + it * 8 + 2] = clock64();
+#endif
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 2 && warp <= 5) {
+        // ---- epilogue: warp w may touch TMEM lanes 32 * (w % 4) .. + 31
+        const int ew = warp & 3;
+        const int row = ew * 32 + lane;
+        int it = 0, s = 0;
+        for (int u = u0; u < u1; u++, it++) {
+            const int vt = u / a.n_gt, gt = u - vt * a.n_gt;
+            const int buf = it & 1;
+            const uint32_t tph = (uint32_t)(it >> 1) & 1u;
+            nvb_mbar_wait(tfull + buf, tph);
+            nvb_tc_fence_after();
+            // the item's MMAs have completed (and, items being waited for in order, those of every
+            // earlier item): its glimpse slot goes back to the producer, and so does the view tile
+            // if this was the last item on it
+            if (warp == 2 && lane == 0) {
+                nvb_mbar_arrive(aempty + s);
+                if (u + 1 < u1 && (u + 1) / a.n_gt != vt) nvb_mbar_arrive(bempty);
+            }
+            if (++s == a_slots) s = 0;
+#if defined(NVB_TC_EXP_STAMPS)
+            if (a.tl != nullptr && blockIdx.x == 0 && it < 60 && tid == 64) a.tl[20000 + it * 8 + 4] = clock64();
+#endif
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256);
+            const int nvalid = min(NT, a.N - vt * NT);
+            // min over columns of -256 * dot + column
+            const int2 b2 = nvb_tc_fold_item<TILEMIN>(taddr, nvalid, [&]() {
+                nvb_tc_fence_before();
+                __syncwarp();
+                if (lane == 0) nvb_mbar_arrive(tempty + buf);
+#if defined(NVB_TC_EXP_STAMPS)
+                if (a.tl != nullptr && blockIdx.x == 0 && it < 60 && tid == 64) a.tl[20000 + it * 8 + 5] = clock64();
+#endif
+            });
+#if defined(NVB_TC_EXP_STAMPS)
+            if (a.tl != nullptr && blockIdx.x == 0 && it < 60 && tid == 64) a.tl[20000 + it * 8 + 6] = clock64();
+#endif
+            const int g = gt * TM + row, best = b2.x;
+            if (TILEMIN) {
+                if (g < a.G) a.tmin[(size_t)g * a.n_vt + vt] = b2;
+            } else if (g < a.G && best != 0x7FFFFFFF) {
+                const int col = best & 255;
+                const int dot = -(best >> 8);
+                const unsigned long long sad = (unsigned long long)((a.sad_const - dot) >> 1);
+                const unsigned long long v = (unsigned long long)(a.view_offset + (long long)vt * NT + col);
+                atomicMin(a.keys + g, (sad << 32) | v);
+            }
         }
     }
     nvb_tc_fence_before();

@@ -22,6 +22,7 @@
 #include "landscape.cuh"
 #include "sampler.cuh"
 #include "step.cuh"
+#include "step_tm.cuh"
 
 #define KEY_NONE NVB_KEY_NONE
 
@@ -102,6 +103,7 @@ struct nvb_engine {
     bool tc_off = false;            // nvb_set_distance_kernel(e, 1): byte-SIMD kernel everywhere
     TcPlanes tc_planes{};
     int tc_K = 0, tc_Kpad = 0, tc_kch = 0, tc_sad_const = 0;
+    bool tc_bs = false;             // view-tile-stationary kernel (k2_tc_bs): rows short enough for the tile + 2 glimpse slots
     uint8_t *d_tc_tab = nullptr;    // sampler tables (SamplerArgs::tc_tab)
     uint8_t *d_tc_level_of = nullptr;   // [256] quantised value -> level index, [256] is-a-level flags (k_tc_encode)
     int *d_tc_bad = nullptr;            // set by k_tc_encode when it meets a value that is not a level
@@ -111,8 +113,10 @@ struct nvb_engine {
     CUtensorMap tm_genc, tm_lenc;
     int *d_spans_tc = nullptr;
     int span_tc_key[3] = {-1, -1, -1};
-    int2 *d_cand = nullptr;         // [Gcap][n_vt] two best candidates per glimpse and view tile (TOP2 kernel)
-    long long cand_cap = 0;
+    int2 *d_tmin = nullptr;         // [Gcap][n_vt] two best keys per tile of the tensor-core kernel (single-launch step, step_tm.cuh)
+    long long tmin_cap = 0;
+    bool want_tmin = false;         // the step-batch being queued ends in k3_step_tm (set by one_step)
+    float *d_pblk_f = nullptr;      // [ceil(n_path / 16)][4] FP32 copy of d_pblk, radius rounded up
     // landscape preparation (landscape.cuh): grain labels of the current landscape
     long long *d_labels = nullptr;
     int *d_grain_area = nullptr;
@@ -165,13 +169,11 @@ struct nvb_engine {
 };
 
 // Step form for small un-sharded libraries, NAVSIM_B200_STEP_FORM (C2, warm, us per step-batch):
-//   3 (default)  K2 | decide | grid-wide tie pass | move + sample                          50.6
-//   5            K2 (tensor-core kernel keeping the two best views per view tile) | decide from those
-//                candidates + move + sample in ONE launch: no pass over the library for ties, two
-//                launches per step.  Measured with the tensor-core kernel (round 2): 35.7 us against
-//                33.9 us for form 3 -- the second-best tracking costs the distance kernel's epilogue
-//                2.5 us and the per-agent decision takes as long inside the big kernel as in its own
-//   4            K2 | decide | move + sample with the tie pass folded into its front       52.3
+//   5 (default)  K2 (tensor-core kernel, leaving the minimum of every view tile) | k3_step_tm: decide
+//                from the tile minima + move + sample in ONE launch (step_tm.cuh); two launches per
+//                step.  Where it does not apply (tm_form()) form 3 runs.
+//   3            K2 | decide | grid-wide tie pass | move + sample
+//   4            K2 | decide | move + sample with the tie pass folded into its front
 //                (needs the whole move+sample grid co-resident, else form 3 is used; the agents
 //                with ties are the critical path either way, so only a launch boundary is saved
 //                and the extra code in the big kernel costs more)
@@ -179,8 +181,8 @@ struct nvb_engine {
 //   2            K2 | decide + cooperative ties | move + sample
 static int step_form()
 {
-    static const int v = getenv("NAVSIM_B200_STEP_FORM") ? atoi(getenv("NAVSIM_B200_STEP_FORM")) : 3;
-    return (v >= 1 && v <= 5) ? v : 3;
+    static const int v = getenv("NAVSIM_B200_STEP_FORM") ? atoi(getenv("NAVSIM_B200_STEP_FORM")) : 5;
+    return (v >= 1 && v <= 5) ? v : 5;
 }
 
 static bool split_step() { return step_form() != 1; }
@@ -301,7 +303,6 @@ static PFN_tmapEncodeTiled tmap_encoder()
 // ---- tensor-core distance kernel: operand planes, buffers, tensor maps ---------------------
 // NAVSIM_B200_NO_TC=1 keeps every configuration on the byte-SIMD kernel (k2_sad_v).
 #define NVB_TC_MIN_G 96   /* fewer glimpses than this leave most of a 128-row MMA tile empty */
-#define NVB_TC_NT 256     /* views per MMA tile (UMMA N) */
 
 static bool use_tc(const nvb_engine *e, long long G)
 {
@@ -309,16 +310,19 @@ static bool use_tc(const nvb_engine *e, long long G)
     return e->tc_ok && !e->tc_off && e->cw == 0.0 && G >= NVB_TC_MIN_G && !off;
 }
 
-// The step after the tensor-core distance kernel as ONE launch (decide from the kernel's two
-// best candidates per view tile + move + sample, step.cuh k3_move_sample<.., CAND>) instead of
-// decide | grid-wide tie pass | move + sample: small un-sharded libraries whose batch the
-// tensor-core kernel scores, sweeps of up to 512 headings, at most 64 view tiles.
-// Step form 5 (NAVSIM_B200_STEP_FORM=5); where it does not apply form 3 runs.
+// The step after the tensor-core distance kernel as ONE launch (step_tm.cuh) instead of
+// decide | grid-wide tie pass | move + sample.  Step form 5 (the default); where it does not
+// apply form 3 runs.
 static bool fused_step(const nvb_engine *e);
-static bool cand_form(const nvb_engine *e)
+static bool long_path_split(const nvb_engine *e);
+static bool tm_form(const nvb_engine *e)
 {
+    const int n_blk = (e->n_path + NVB_PATH_BLOCK - 1) / NVB_PATH_BLOCK;
     return step_form() == 5 && fused_step(e) && use_tc(e, (long long)e->B * e->A) && e->lenc_valid && e->tc_lib_ok &&
-           e->A <= NVB_STEP_MAX_A_SMEM && (e->N + NVB_TC_NT - 1) / NVB_TC_NT <= 64;
+           !e->p2p_on && e->view_offset == 0 && e->n_total == e->N && e->R > 0 && e->P <= NVB_PTAB_MAX &&
+           e->A <= NVB_TM_MAX_A && (e->N + NVB_TC_NT - 1) / NVB_TC_NT <= NVB_TM_MAX_VT &&
+           e->d_pblk_f != nullptr && n_blk <= 4096 && !long_path_split(e) && e->cvf * e->step_size <= e->max_dist &&
+           getenv("NAVSIM_B200_NO_PATH_BLOCKS") == nullptr;
 }
 
 // Thermometer planes of the V-channel quantisation table (distance_tc.cuh): levels = the
@@ -367,8 +371,10 @@ static int build_tc_planes(nvb_engine *e, const uint8_t *lut_v)
     e->tc_planes = pl;
     e->tc_K = pl.n_planes * e->P;
     const int k64 = nvb_round_up(e->tc_K, 64), k128 = nvb_round_up(e->tc_K, 128);
-    // 128-byte K chunks (fewer, larger TMA transactions) unless the zero padding gets heavy
-    e->tc_kch = (k128 * 4 <= e->tc_K * 5) ? 128 : 64;
+    // short rows: the view tile stays resident in shared memory (k2_tc_bs, 64-byte chunks);
+    // otherwise 128-byte K chunks (fewer, larger TMA transactions) unless the zero padding gets heavy
+    e->tc_bs = nvb_tcbs_slots(k64 / NVB_TCBS_KCH) >= 2 && getenv("NAVSIM_B200_TC_STREAM") == nullptr;
+    e->tc_kch = e->tc_bs ? 64 : (k128 * 4 <= e->tc_K * 5) ? 128 : 64;
     e->tc_Kpad = e->tc_kch == 128 ? k128 : k64;
     e->tc_sad_const = e->P * sum_w;
     // 32-bit keys of the epilogue: 256 * |dot| + column must stay below 2^31
@@ -509,7 +515,7 @@ extern "C" void nvb_engine_destroy(nvb_engine *e)
                     e->ag.budget, e->ag.nav_frames, e->ag.err_sum, e->ag.err_n, e->ag.coverage,
                     e->ag.stepped, e->d_step, e->log_best, e->log_pose, e->log_sfam, e->log_afam,
                     e->d_poses0, e->d_budget0, e->d_spans, e->d_pending, e->d_dmin2, e->d_pblk, e->d_pblk2,
-                    e->d_tc_tab, e->d_tc_level_of, e->d_genc, e->d_lenc, e->d_spans_tc, e->d_tc_bad, e->d_cand, e->d_labels, e->d_grain_area};
+                    e->d_tc_tab, e->d_tc_level_of, e->d_genc, e->d_lenc, e->d_spans_tc, e->d_tc_bad, e->d_tmin, e->d_pblk_f, e->d_labels, e->d_grain_area};
     for (int i = 0; i < NVB_P2P_MAX_RANKS; i++)
         if (e->p2p_opened[i]) cudaIpcCloseMemHandle(e->p2p_opened[i]);
     free_dev(e->d_xarea); free_dev(e->d_p2p_seq); free_dev(e->d_p2p_err);
@@ -790,11 +796,15 @@ static int launch_sampler(nvb_engine *e, const SamplerArgs &sa, int nblocks, int
     const int nplanes = sa.need_hs ? 3 : 1;
     const size_t smem = e->R > 0 ? nvb_sampler_smem(e->BW, e->BH, nplanes, sa.A)
                                  : nvb_sampler_smem(0, 0, 0, sa.A);
+#ifndef NVB_DEV_MIN
     if (sa.need_hs) return launch_sampler_t<true, 0, 0>(e, sa, nblocks, smem, slices);
+#endif
     // sensor-pixel footprints the reference's drivers use get an unrolled sampling loop
     if (e->ph == 4 && e->pw == 2) return launch_sampler_t<false, 4, 2>(e, sa, nblocks, smem, slices);
+#ifndef NVB_DEV_MIN
     if (e->ph == 2 && e->pw == 2) return launch_sampler_t<false, 2, 2>(e, sa, nblocks, smem, slices);
     if (e->ph == 1 && e->pw == 1) return launch_sampler_t<false, 1, 1>(e, sa, nblocks, smem, slices);
+#endif
     return launch_sampler_t<false, 0, 0>(e, sa, nblocks, smem, slices);
 }
 
@@ -891,11 +901,11 @@ static int launch_dist_cpr(nvb_engine *e, const DistArgs &da)
     return launch_dist_cfg<16, 4, 16, CPR>(e, da);
 }
 
-template <int KCH, int STAGES, bool TOP2>
+template <int KCH, int STAGES, bool TILEMIN>
 static int launch_tc_cfg(nvb_engine *e, TcArgs ta)
 {
     using C = TcCfg<KCH, NVB_TC_NT, STAGES>;
-    auto kern = k2_tc<KCH, NVB_TC_NT, STAGES, TOP2>;
+    auto kern = k2_tc<KCH, NVB_TC_NT, STAGES, TILEMIN>;
     static bool attr_set[64] = {false};
     if (!attr_set[e->device & 63]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -928,6 +938,45 @@ static int launch_tc_cfg(nvb_engine *e, TcArgs ta)
     return NVB_OK;
 }
 
+template <bool TILEMIN>
+static int launch_tc_bs(nvb_engine *e, TcArgs ta)
+{
+    auto kern = k2_tc_bs<TILEMIN>;
+    const int kchunks = e->tc_Kpad / NVB_TCBS_KCH;
+    const int a_stages = nvb_tcbs_slots(kchunks);   // glimpse slots (whole items) beside the resident view tile
+    const int smem = nvb_tcbs_smem(kchunks, a_stages);
+    static int attr_set[64] = {0};
+    if (attr_set[e->device & 63] < smem) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[e->device & 63] = smem;
+    }
+    const int n_gt = (ta.G + NVB_TC_TM - 1) / NVB_TC_TM, n_vt = (ta.N + NVB_TC_NT - 1) / NVB_TC_NT;
+    const long long items = (long long)n_gt * n_vt;
+    const int n_cta = (int)(items < e->sm_count ? items : e->sm_count);
+    if (!(e->span_tc_key[0] == n_gt && e->span_tc_key[1] == n_vt && e->span_tc_key[2] == n_cta)) {
+        std::vector<int> spans(n_cta + 1);
+        const long long base = items / n_cta, rem = items % n_cta;
+        long long u = 0;
+        for (int c = 0; c < n_cta; c++) { spans[c] = (int)u; u += base + (c < rem ? 1 : 0); }
+        spans[n_cta] = (int)items;
+        int rc = alloc_dev(&e->d_spans_tc, (size_t)n_cta + 1);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(e->d_spans_tc, spans.data(), sizeof(int) * (n_cta + 1), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));   // spans is a stack vector
+        e->span_tc_key[0] = n_gt; e->span_tc_key[1] = n_vt; e->span_tc_key[2] = n_cta;
+        e->graph_dirty = true;
+    }
+    ta.n_vt = n_vt;
+    ta.n_gt = n_gt;
+    ta.vt_major = 1;
+    ta.kchunks = kchunks;
+    ta.spans = e->d_spans_tc;
+    CK(launch_seq(kern, dim3((unsigned)n_cta), dim3(NVB_TCBS_THREADS), (size_t)smem, e->stream, e->tm_genc, e->tm_lenc, ta, a_stages));
+    e->launches++;
+    CK(cudaGetLastError());
+    return NVB_OK;
+}
+
 // K2 on the tensor cores.  encode_glimpses: the glimpse planes were not written by the sampler
 // (queries uploaded from the host): encode them from the V plane first.
 static int launch_distance_tc(nvb_engine *e, int G, bool bump_step, bool encode_glimpses)
@@ -950,14 +999,16 @@ static int launch_distance_tc(nvb_engine *e, int G, bool bump_step, bool encode_
     ta.epoch = (bump_step && e->p2p_on) ? e->d_p2p_seq : nullptr;
     ta.pdl_early = (bump_step && early_trigger()) ? 1 : 0;
     ta.tl = bump_step ? e->d_tl : nullptr;
-    ta.cand = nullptr;
-    if (bump_step && cand_form(e) && e->d_cand != nullptr) {
-        // the candidate-based step: the two best views per glimpse and view tile (step.cuh;
-        // the array is allocated by prepare_step_buffers before the step arguments are built)
-        ta.cand = e->d_cand;
+    ta.tmin = nullptr;
+    if (bump_step && e->want_tmin) {
+        // the single-launch step: the minimum of every view tile instead of the packed keys (the
+        // array is allocated by prepare_step_buffers before the step arguments are built)
+        ta.tmin = e->d_tmin;
+        if (e->tc_bs) return launch_tc_bs<true>(e, ta);
         if (e->tc_kch == 128) return launch_tc_cfg<128, 4, true>(e, ta);
         return launch_tc_cfg<64, 8, true>(e, ta);
     }
+    if (e->tc_bs) return launch_tc_bs<false>(e, ta);
     if (e->tc_kch == 128) return launch_tc_cfg<128, 4, false>(e, ta);
     return launch_tc_cfg<64, 8, false>(e, ta);
 }
@@ -1019,13 +1070,25 @@ static int launch_distance(nvb_engine *e, int G, bool bump_step = false, bool gl
     static const bool hsv_untiled = getenv("NAVSIM_B200_HSV_UNTILED") != nullptr;
     if (e->cw != 0.0 && G >= 16 && !hsv_untiled) {
         switch (e->cpr) {
-        case 1: return launch_hsv_tiled<1>(e, da);
-        case 2: return launch_hsv_tiled<2>(e, da);
-        case 3: return launch_hsv_tiled<3>(e, da);
-        case 4: return launch_hsv_tiled<4>(e, da);
+    #ifndef NVB_DEV_MIN
+    case 1: return launch_hsv_tiled<1>(e, da);
+#endif
+    #ifndef NVB_DEV_MIN
+    case 2: return launch_hsv_tiled<2>(e, da);
+#endif
+    #ifndef NVB_DEV_MIN
+    case 3: return launch_hsv_tiled<3>(e, da);
+#endif
+    #ifndef NVB_DEV_MIN
+    case 4: return launch_hsv_tiled<4>(e, da);
+#endif
         case 5: return launch_hsv_tiled<5>(e, da);
-        case 7: return launch_hsv_tiled<7>(e, da);
-        case 8: return launch_hsv_tiled<8>(e, da);
+    #ifndef NVB_DEV_MIN
+    case 7: return launch_hsv_tiled<7>(e, da);
+#endif
+    #ifndef NVB_DEV_MIN
+    case 8: return launch_hsv_tiled<8>(e, da);
+#endif
         }
         return fail(NVB_E_INVALID, "unsupported chunk count %d", e->cpr);
     }
@@ -1050,13 +1113,25 @@ static int launch_distance(nvb_engine *e, int G, bool bump_step = false, bool gl
         return NVB_OK;
     }
     switch (e->cpr) {
+#ifndef NVB_DEV_MIN
     case 1: return launch_dist_cpr<1>(e, da);
+#endif
+#ifndef NVB_DEV_MIN
     case 2: return launch_dist_cpr<2>(e, da);
+#endif
+#ifndef NVB_DEV_MIN
     case 3: return launch_dist_cpr<3>(e, da);
+#endif
+#ifndef NVB_DEV_MIN
     case 4: return launch_dist_cpr<4>(e, da);
+#endif
     case 5: return launch_dist_cpr<5>(e, da);
+#ifndef NVB_DEV_MIN
     case 7: return launch_dist_cpr<7>(e, da);
+#endif
+#ifndef NVB_DEV_MIN
     case 8: return launch_dist_cpr<8>(e, da);
+#endif
     }
     return fail(NVB_E_INVALID, "unsupported chunk count %d", e->cpr);
 }
@@ -1241,6 +1316,18 @@ static int set_path(nvb_engine *e, const double *path, int n)
     }
     if ((rc = alloc_dev(&e->d_pblk, (size_t)4 * nb))) return rc;
     CK(cudaMemcpy(e->d_pblk, blk.data(), sizeof(double) * 4 * nb, cudaMemcpyHostToDevice));
+    // FP32 copy for the single-launch step's prefilter (step_tm.cuh): the radius also covers the
+    // rounding of the centre, and is rounded up
+    std::vector<float> blkf((size_t)4 * nb);
+    for (int j = 0; j < nb; j++) {
+        const float cxf = (float)blk[4 * j], cyf = (float)blk[4 * j + 1];
+        const double rr = blk[4 * j + 2] + fabs(blk[4 * j] - (double)cxf) + fabs(blk[4 * j + 1] - (double)cyf);
+        float rf = (float)rr;
+        while ((double)rf < rr) rf = nextafterf(rf, INFINITY);
+        blkf[4 * j] = cxf; blkf[4 * j + 1] = cyf; blkf[4 * j + 2] = nextafterf(rf, INFINITY); blkf[4 * j + 3] = 0.0f;
+    }
+    if ((rc = alloc_dev(&e->d_pblk_f, (size_t)4 * nb))) return rc;
+    CK(cudaMemcpy(e->d_pblk_f, blkf.data(), sizeof(float) * 4 * nb, cudaMemcpyHostToDevice));
     // second level for long paths: one circle per NVB_PATH_GROUP blocks
     const int ng = (nb + NVB_PATH_GROUP - 1) / NVB_PATH_GROUP, gpts = NVB_PATH_GROUP * NVB_PATH_BLOCK;
     std::vector<double> grp((size_t)4 * ng);
@@ -1540,16 +1627,16 @@ static int ensure_tc_library(nvb_engine *e);
 
 // Buffers the step kernels are handed by value must exist before the arguments are built:
 // the encoded library (decides whether the tensor-core kernel runs) and, for the
-// candidate-based step, the candidate array.
+// single-launch step, the tile-minimum array.
 static void prepare_step_buffers(nvb_engine *e)
 {
     if (!use_tc(e, (long long)e->B * e->A) || e->N <= 0) return;
     if (ensure_tc_library(e) != NVB_OK) return;
-    if (!cand_form(e)) return;
+    if (!tm_form(e)) return;
     const long long n_vt = (e->N + NVB_TC_NT - 1) / NVB_TC_NT, need = (long long)e->Gcap * n_vt;
-    if (need > e->cand_cap) {
-        if (alloc_dev(&e->d_cand, (size_t)need) != NVB_OK) { e->d_cand = nullptr; e->cand_cap = 0; return; }
-        e->cand_cap = need;
+    if (need > e->tmin_cap) {
+        if (alloc_dev(&e->d_tmin, (size_t)need) != NVB_OK) { e->d_tmin = nullptr; e->tmin_cap = 0; return; }
+        e->tmin_cap = need;
         e->graph_dirty = true;
     }
 }
@@ -1588,7 +1675,8 @@ static StepArgs make_step_args(nvb_engine *e, int fake, int log_afam)
     s.pdl_early = early_trigger() ? 1 : 0;
     s.tl = e->d_tl;
     s.out_best = e->zc_best; s.out_poses = e->zc_pose; s.out_sfam = e->zc_fam;
-    s.cand = e->d_cand;
+    s.tmin = e->d_tmin;
+    s.pblk_f = e->d_pblk_f;
     s.n_vt = (e->N + NVB_TC_NT - 1) / NVB_TC_NT;
     s.sad_const = e->tc_sad_const;
     s.p2p = e->p2p;
@@ -1659,7 +1747,7 @@ static int launch_k31_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa,
 static int effective_form(const nvb_engine *e)
 {
     int f = step_form();
-    if (f == 5) f = 3;   // (the candidate form is chosen by cand_form(); everything else runs as form 3)
+    if (f == 5) f = 3;   // (the single-launch form is chosen by tm_form(); everything else runs as form 3)
     if (f == 4 && e->ms_capacity >= 0 && e->B > e->ms_capacity) return 3;
     return f;
 }
@@ -1716,12 +1804,13 @@ static int launch_k3ms_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa
     return NVB_OK;
 }
 
-template <bool HS, int PH, int PW>
-static int launch_k3cand_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa, size_t smem)
+template <int PH, int PW>
+static int launch_k3tm_t(nvb_engine *e, const StepArgs &s, SamplerArgs sa, size_t smem)
 {
+    smem = (size_t)nvb_round_up((int)smem, 16) + sizeof(int2) * (size_t)s.A * s.n_vt;   // + the agent's tile candidates
     static size_t attr_set[64] = {0};
     size_t &cur = attr_set[e->device & 63];
-    auto kern = k3_move_sample<HS, PH, PW, false, true>;
+    auto kern = k3_step_tm<PH, PW>;
     if (smem > cur) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
@@ -1729,6 +1818,7 @@ static int launch_k3cand_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &
     const long long items = (long long)e->A * e->P;
     const long long w128 = ((items + 127) / 128) * 128, w160 = ((items + 159) / 160) * 160;
     const int threads = w160 < w128 ? NVB_MS_MAX_THREADS : NVB_STEP_THREADS;
+    sa.keys = nullptr;   // the packed keys are not used in this form: nothing to reset
     CK(launch_seq(kern, dim3(e->B), dim3(threads), smem, e->stream, e->tmap, s, sa));
     e->launches += 1;
     CK(cudaGetLastError());
@@ -1736,22 +1826,28 @@ static int launch_k3cand_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &
 }
 
 // [decide + cooperative tie scan] then [move + sample next]
-static int launch_k3_split(nvb_engine *e, const StepArgs &s)
+static int launch_k3_split(nvb_engine *e, const StepArgs &s, bool tm)
 {
     const SamplerArgs sa = agent_sampler_args(e);
     const int nplanes = sa.need_hs ? 3 : 1;
     const size_t smem = e->R > 0 ? nvb_sampler_smem(e->BW, e->BH, nplanes, sa.A)
                                  : nvb_sampler_smem(0, 0, 0, sa.A);
-    if (cand_form(e) && e->d_cand != nullptr) {   // (need_hs implies chem_weight > 0: never the tensor-core kernel)
-        if (e->ph == 4 && e->pw == 2) return launch_k3cand_t<false, 4, 2>(e, s, sa, smem);
-        if (e->ph == 2 && e->pw == 2) return launch_k3cand_t<false, 2, 2>(e, s, sa, smem);
-        if (e->ph == 1 && e->pw == 1) return launch_k3cand_t<false, 1, 1>(e, s, sa, smem);
-        return launch_k3cand_t<false, 0, 0>(e, s, sa, smem);
+    if (tm) {   // K2 left tile minima (chem_weight 0: V plane only)
+        if (e->ph == 4 && e->pw == 2) return launch_k3tm_t<4, 2>(e, s, sa, smem);
+#ifndef NVB_DEV_MIN
+        if (e->ph == 2 && e->pw == 2) return launch_k3tm_t<2, 2>(e, s, sa, smem);
+        if (e->ph == 1 && e->pw == 1) return launch_k3tm_t<1, 1>(e, s, sa, smem);
+#endif
+        return launch_k3tm_t<0, 0>(e, s, sa, smem);
     }
+#ifndef NVB_DEV_MIN
     if (sa.need_hs) return launch_k3ms_t<true, 0, 0>(e, s, sa, smem);
+#endif
     if (e->ph == 4 && e->pw == 2) return launch_k3ms_t<false, 4, 2>(e, s, sa, smem);
+#ifndef NVB_DEV_MIN
     if (e->ph == 2 && e->pw == 2) return launch_k3ms_t<false, 2, 2>(e, s, sa, smem);
     if (e->ph == 1 && e->pw == 1) return launch_k3ms_t<false, 1, 1>(e, s, sa, smem);
+#endif
     return launch_k3ms_t<false, 0, 0>(e, s, sa, smem);
 }
 
@@ -1761,10 +1857,14 @@ static int launch_k31(nvb_engine *e, const StepArgs &s)
     const int nplanes = sa.need_hs ? 3 : 1;
     const size_t smem = e->R > 0 ? nvb_sampler_smem(e->BW, e->BH, nplanes, sa.A)
                                  : nvb_sampler_smem(0, 0, 0, sa.A);
+#ifndef NVB_DEV_MIN
     if (sa.need_hs) return launch_k31_t<true, 0, 0>(e, s, sa, smem);
+#endif
     if (e->ph == 4 && e->pw == 2) return launch_k31_t<false, 4, 2>(e, s, sa, smem);
+#ifndef NVB_DEV_MIN
     if (e->ph == 2 && e->pw == 2) return launch_k31_t<false, 2, 2>(e, s, sa, smem);
     if (e->ph == 1 && e->pw == 1) return launch_k31_t<false, 1, 1>(e, s, sa, smem);
+#endif
     return launch_k31_t<false, 0, 0>(e, s, sa, smem);
 }
 
@@ -1853,13 +1953,18 @@ static bool fused_step(const nvb_engine *e)
 static int one_step(nvb_engine *e, const StepArgs &s, bool sample_next = true)
 {
     int rc;
-    if ((rc = phase1(e))) return rc;
+    // K2 leaves tile minima instead of packed keys only when k3_step_tm is what reads them
+    e->want_tmin = sample_next && fused_step(e) && split_step() && tm_form(e) && e->d_tmin != nullptr;
+    rc = phase1(e);
+    const bool tm = e->want_tmin;
+    e->want_tmin = false;
+    if (rc) return rc;
     if (fused_step(e)) {
         if (sample_next) {
             // measured on the 1024-agent workload: one fused launch (69 us/step) beats
             // [decide + cooperative ties] + [move + sample] (79 us/step); the split form
             // stays available as a tuning knob
-            if ((rc = split_step() ? launch_k3_split(e, s) : launch_k31(e, s))) return rc;
+            if ((rc = split_step() ? launch_k3_split(e, s, tm) : launch_k31(e, s))) return rc;
             e->glimpses_pending = true;
             return NVB_OK;
         }
@@ -1937,7 +2042,7 @@ static int run_steps(nvb_engine *e, int nsteps, int fake, int log_afam, bool eag
         // launches per step-batch: K2, decide, ties, move+sample | K1, K2, decide, ties, move
         // (+2 for the long-path move, +2 for the NVLink exchanges)
         const int ef = effective_form(e);
-        const int per_step = fused_step(e) ? ((cand_form(e) && e->d_cand) ? 2 : ef == 3 ? 4 : (ef == 2 || ef == 4) ? 3 : 2)
+        const int per_step = fused_step(e) ? ((tm_form(e) && e->d_tmin && split_step()) ? 2 : ef == 3 ? 4 : (ef == 2 || ef == 4) ? 3 : 2)
                                            : 5 + (long_path_split(e) && !fake ? 2 : 0);
         for (int i = done; i < nsteps; i++) {
             CK(cudaGraphLaunch(e->graph_exec, e->stream));
@@ -2267,7 +2372,7 @@ extern "C" int nvb_debug_timeline(nvb_engine *e, int nsteps, long long *out)
     int rc = check_step_ready(e, 0);
     if (rc) return rc;
     CK(cudaSetDevice(e->device));
-    const size_t n = (size_t)4 * NVB_TL_CTAS * 3;
+    const size_t n = (size_t)6 * NVB_TL_CTAS * 3;   // kernels 0..3 + two slots of k3_step_tm checkpoints
     CK(cudaMalloc(&e->d_tl, sizeof(long long) * n));
     CK(cudaMemsetAsync(e->d_tl, 0, sizeof(long long) * n, e->stream));
     e->graph_dirty = true;

@@ -156,10 +156,11 @@ struct StepArgs {
     double *out_sfam;            // [B]
     double cover_thr2;           // largest double whose sqrt is <= coverage_factor * step_size (host)
     P2PArgs p2p;                 // exchange descriptor (view shards over NVLink); world == 0: none
-    // candidate-based decide (tensor-core distance kernel, TOP2): [B*A][n_vt] the two smallest
-    // tile-local keys (-256 * dot + column; 0x7FFFFFFF = none) of every glimpse and view tile
-    const int2 *cand;
-    int n_vt, sad_const;         // view tiles of 256 views; C of SAD = (C - dot) / 2
+    // single-launch step (step_tm.cuh; tensor-core distance kernel, TILEMIN): [B*A][n_vt] the
+    // smallest tile-local key (-256 * dot + column; 0x7FFFFFFF = none) of every glimpse and view tile
+    const int2 *tmin;
+    int n_vt, sad_const;         // view tiles of NVB_TC_NT views; C of SAD = (C - dot) / 2
+    const float *pblk_f;         // [blocks][4] FP32 copy of pblk, radius rounded up (step_tm.cuh prefilter)
 };
 
 #define NVB_PATH_BLOCK 16      /* path points per bounding circle (update_error prefilter) */
@@ -374,18 +375,8 @@ __device__ __forceinline__ void nvb_decide(const StepArgs &a, int b, unsigned lo
     }
 }
 
-// decide from candidates: the tensor-core distance kernel (TOP2) has left, per glimpse and
-// view tile, the two smallest (difference, view) pairs.  Per heading: the minimum over the tiles
-// and its first view (tiles are in view order and a tile's smallest key has the lowest column, so
-// this is the lowest view index, as the packed-key minimum gives it); headings tied at the
-// step's integer minimum get the exact FP64 difference of EVERY view that attains it
-// (SURVEY.md H1): the best of each tile, its runner-up if it ties too, and -- only when a
-// tile's first two both tie -- the rest of that tile, rescanned by the whole CTA.  No pass over
-// the library, no second launch.  Results: s_exact[k] (k < NVB_STEP_MAX_A_SMEM) / a.exact.
-#define NVB_CAND_JOBS 24
-// (not inlined, and handed plain pointers rather than the argument struct -- whose address
-// would force a copy of it into local memory: the candidate code sits in front of the
-// register-tight move+sample kernel.  V plane only: the tensor-core kernel implies chem_weight 0.)
+// Row helpers of the tie passes (V plane only: chem_weight 0).
+// (not inlined, handed plain pointers: they sit in front of register-tight kernels)
 __device__ __noinline__ unsigned long long nvb_exact_bits(const uint8_t *qrow, const uint8_t *frow, int nc,
                                                           const double *div255)
 {
@@ -415,90 +406,6 @@ __device__ __noinline__ unsigned nvb_pair_score_v(const uint8_t *qrow, const uin
     }
     return sum;
 }
-__device__ __forceinline__ unsigned nvb_cand_sad(const StepArgs &a, int key)
-{
-    return (unsigned)((a.sad_const + (key >> 8)) >> 1);   // key = -256 * dot + column, SAD = (C - dot) / 2
-}
-
-__device__ __forceinline__ void nvb_decide_cand(const StepArgs &a, int b, unsigned long long *s_exact,
-                                                const double *div255)
-{
-    const int tid = threadIdx.x;
-    const int nc = a.Ppad / 16;
-    __shared__ unsigned s_minsad;
-    __shared__ int s_ntied, s_njobs;
-    __shared__ unsigned s_hsad[NVB_STEP_MAX_A_SMEM];
-    __shared__ int s_hview[NVB_STEP_MAX_A_SMEM];
-    __shared__ int s_jobs[NVB_CAND_JOBS][3];
-    if (tid == 0) { s_minsad = 0xFFFFFFFFu; s_ntied = 0; s_njobs = 0; }
-    __syncthreads();
-    for (int k = tid; k < a.A; k += blockDim.x) {
-        const int2 *c = a.cand + ((size_t)b * a.A + k) * a.n_vt;
-        unsigned best_sad = 0xFFFFFFFFu;
-        int best_view = -1;
-        for (int t = 0; t < a.n_vt; t++) {
-            const int key = c[t].x;
-            if (key == 0x7FFFFFFF) continue;
-            const unsigned sad = nvb_cand_sad(a, key);
-            if (sad < best_sad) { best_sad = sad; best_view = t * 256 + (key & 255); }
-        }
-        if (k < NVB_STEP_MAX_A_SMEM) { s_hsad[k] = best_sad; s_hview[k] = best_view; }
-        atomicMin(&s_minsad, best_sad);
-    }
-    __syncthreads();
-    const unsigned M = s_minsad;
-    for (int k = tid; k < a.A && k < NVB_STEP_MAX_A_SMEM; k += blockDim.x)
-        if (s_hsad[k] == M) atomicAdd(&s_ntied, 1);
-    __syncthreads();
-    const bool have_ties = s_ntied > 1;
-    for (int k = tid; k < a.A && k < NVB_STEP_MAX_A_SMEM; k += blockDim.x) {
-        const size_t g = (size_t)b * a.A + k;
-        unsigned long long eb = NVB_EXACT_NONE;
-        if (s_hview[k] >= 0) {
-            if (!(have_ties && s_hsad[k] == M)) {
-                eb = nvb_exact_bits(a.gv + g * a.Ppad, a.lv + (size_t)s_hview[k] * a.Ppad, nc, div255);
-            } else {
-                const int2 *c = a.cand + g * a.n_vt;
-                for (int t = 0; t < a.n_vt; t++) {
-                    const int2 kk = c[t];
-                    if (kk.x == 0x7FFFFFFF || nvb_cand_sad(a, kk.x) != M) continue;
-                    unsigned long long e = nvb_exact_bits(a.gv + g * a.Ppad, a.lv + (size_t)(t * 256 + (kk.x & 255)) * a.Ppad, nc, div255);
-                    eb = e < eb ? e : eb;
-                    if (kk.y == 0x7FFFFFFF || nvb_cand_sad(a, kk.y) != M) continue;
-                    e = nvb_exact_bits(a.gv + g * a.Ppad, a.lv + (size_t)(t * 256 + (kk.y & 255)) * a.Ppad, nc, div255);
-                    eb = e < eb ? e : eb;
-                    // both of this tile's candidates tie: later views of the tile may tie as well
-                    const int slot = atomicAdd(&s_njobs, 1);
-                    if (slot < NVB_CAND_JOBS) {
-                        s_jobs[slot][0] = k; s_jobs[slot][1] = t; s_jobs[slot][2] = (kk.y & 255) + 1;
-                    } else {
-                        for (int col = (kk.y & 255) + 1; col < 256 && t * 256 + col < a.N; col++) {
-                            const size_t fo = (size_t)(t * 256 + col) * a.Ppad;
-                            if (nvb_pair_score_v(a.gv + g * a.Ppad, a.lv + fo, nc) == M) {
-                                e = nvb_exact_bits(a.gv + g * a.Ppad, a.lv + fo, nc, div255);
-                                eb = e < eb ? e : eb;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        s_exact[k] = eb;
-    }
-    __syncthreads();
-    const int njobs = min(s_njobs, NVB_CAND_JOBS);
-    for (int j = 0; j < njobs; j++) {
-        const int k = s_jobs[j][0], t = s_jobs[j][1];
-        const size_t g = (size_t)b * a.A + k;
-        for (int col = s_jobs[j][2] + tid; col < 256 && t * 256 + col < a.N; col += blockDim.x) {
-            const size_t fo = (size_t)(t * 256 + col) * a.Ppad;
-            if (nvb_pair_score_v(a.gv + g * a.Ppad, a.lv + fo, nc) == M)
-                atomicMin(s_exact + k, nvb_exact_bits(a.gv + g * a.Ppad, a.lv + fo, nc, div255));
-        }
-    }
-    __syncthreads();
-}
-
 // move: argmax, pose update, update_error, end test, log.  s_exact (shared, may be
 // nullptr) / a.exact hold the exact differences.  Returns through *pose_out the
 // new pose and whether the agent will take another step (status still 0 and
@@ -1150,18 +1057,12 @@ __device__ __forceinline__ void nvb_tie_wait(const StepArgs &a, int b, int n_ite
     __threadfence();
 }
 
-// CAND: the whole step after the distance kernel in this one launch -- decide from the
-// candidates the tensor-core kernel left (nvb_decide_cand), then move and sample.
-template <bool NEED_HS, int PH, int PW, bool TIES, bool CAND = false>
+template <bool NEED_HS, int PH, int PW, bool TIES>
 __global__ void __launch_bounds__(NVB_MS_MAX_THREADS, 7)   // 1024 agents = 7 CTAs per SM: one wave
 k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs sa)
 {
     nvb_tl_stamp(a.tl, 3, 0);
     if (a.pdl_early) nvb_grid_dep_launch();
-    __shared__ unsigned long long s_exact_c[CAND ? NVB_STEP_MAX_A_SMEM : 1];
-    __shared__ double s_div_c[CAND ? 256 : 1];
-    if (CAND)
-        for (int k = threadIdx.x; k < 256; k += blockDim.x) s_div_c[k] = a.div255[k];   // constant table
     extern __shared__ __align__(128) uint8_t smem_k3ms[];
     const SamplerSmem L = nvb_sampler_layout<NEED_HS>(sa.w, sa.A, smem_k3ms);
     // constant data while the tie pass drains: quantisation tables and heading offsets ->
@@ -1186,28 +1087,7 @@ k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs
     if (sa.dbg && threadIdx.x == 0) sa.dbg[b * 8 + 1] = clock64();
     int stepped, n_items = 0;
     MovePre pre;
-    if (CAND) {
-        // as k3_decide: thread 0 alone decides whether the agent takes part (a failure the sampler
-        // parked for THIS step becomes its status now), then the decision from the candidates
-        __shared__ int s_active_c;
-        if (threadIdx.x == 0) {
-            const int pf = (a.pending_fail != nullptr) ? a.pending_fail[b] : 0;
-            const int status = a.ag.status[b], completed = a.ag.completed[b], budget = a.ag.budget[b];
-            if (pf != 0) {
-                a.ag.status[b] = pf;
-                a.pending_fail[b] = 0;
-            }
-            s_active_c = (pf == 0) && status == 0 && completed < budget;
-        }
-        __syncthreads();
-        stepped = s_active_c;
-        if (!stepped) {
-            nvb_log_idle(a, b);
-            return;
-        }
-        nvb_decide_cand(a, b, s_exact_c, s_div_c);
-        pre = nvb_move_preload(a, b, s_exact_c);
-    } else {
+    {
         // everything this agent's move needs, requested before the first branch on any of it
         stepped = a.ag.stepped[b];
         n_items = TIES ? a.tie_count[0] : 0;
@@ -1222,7 +1102,7 @@ k3_move_sample(const __grid_constant__ CUtensorMap tmap, StepArgs a, SamplerArgs
             pre = nvb_move_preload(a, b, nullptr);
         }
     }
-    const unsigned long long *s_ex = CAND ? s_exact_c : nullptr;
+    const unsigned long long *s_ex = nullptr;
     if (TIES && stepped == 2) {
         nvb_tie_wait(a, b, n_items);
         if (a.A <= 32 && threadIdx.x < a.A) pre.eb = __ldcg(a.exact + (size_t)b * a.A + threadIdx.x);

@@ -456,13 +456,17 @@ class NavEngine(object):
     def time_distance_kernel(self, reps=20):
         return float(self._lib.nvb_time_distance_kernel(self._h, int(reps)))
 
-    def timeline(self, nsteps=8):
+    def timeline(self, nsteps=8, raw=False):
         """Tuning aid: runs `nsteps` step-batches as step() does and returns, for the last one,
         {kernel: (first CTA resident, first dependency met, last CTA done)} in microseconds
-        since the step-batch's first stamp, plus 'span' = the whole step-batch."""
-        out = np.zeros((4, 2048, 3), np.int64)
+        since the step-batch's first stamp, plus 'span' = the whole step-batch.
+        raw=True: the per-CTA stamps [kernel][cta][3] in ns (0 = not stamped)."""
+        out = np.zeros((6, 2048, 3), np.int64)
         check(self._lib.nvb_debug_timeline(self._h, int(nsteps), ptr(out)))
-        names = ["k2", "k3_decide", "k3_ties", "k3_move_sample"]
+        if raw:
+            return out
+        # (slots 4 and 5 hold per-CTA checkpoints of the single-launch step kernel, k3_step_tm)
+        names = ["k2", "k3_decide", "k3_ties", "k3_step_tm" if out[4].any() else "k3_move_sample"]
         res = {}
         t0 = None
         for k, name in enumerate(names):

@@ -15,7 +15,7 @@ VARIANTS = [
     {"NAVSIM_B200_STEP_FORM": "1"},          # decide + ties + move + sample in one launch
     {"NAVSIM_B200_STEP_FORM": "2"},          # cooperative tie queue
     {"NAVSIM_B200_STEP_FORM": "4"},          # tie pass folded into move + sample
-    {"NAVSIM_B200_STEP_FORM": "5"},          # tensor-core kernel keeps two candidates per tile; decide + move + sample in one launch
+    {"NAVSIM_B200_STEP_FORM": "3"},          # K2 | decide | grid-wide tie pass | move + sample (the default is 5: K2 | k3_step_tm)
     {"NAVSIM_B200_NO_TC": "1"},              # byte-SIMD distance kernel everywhere
     {"NAVSIM_B200_NO_PDL": "1"},             # plain stream order, no programmatic dependent launch
     {"NAVSIM_B200_NO_TMA": "1"},             # landscape window gathered from global memory

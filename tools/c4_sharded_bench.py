@@ -68,6 +68,8 @@ def main():
     dt = time.perf_counter() - t0
     k2_ms = eng.time_distance_kernel(20)
     st = eng.state(coverage=False)
+    eng.rewind()
+    tl = eng.timeline(8)   # (every rank queues the same steps: the exchanges need all of them)
     if world > 1:
         t = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -81,7 +83,8 @@ def main():
             "k2_us": k2_ms * 1e3, "k2_hbm_gbs": cnt * P / (k2_ms * 1e-3) / 1e9,
             "exchange": "NVLink P2P (k_p2p_min)" if world > 1 else "none",
             "p2p_error": eng.p2p_error() if world > 1 else 0,
-            "agents_still_running": int((st["status"] == 0).sum())}))
+            "agents_still_running": int((st["status"] == 0).sum()),
+            "step_timeline_us": {k: [round(x, 2) for x in v] if isinstance(v, tuple) else round(v, 2) for k, v in tl.items()}}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -147,6 +147,87 @@ static void run_tc(Ctx &c, const TcPlanes &pl, const uint8_t *d_level_of, const 
     cudaFree(d_a); cudaFree(d_b); cudaFree(d_spans);
 }
 
+// the view-tile-stationary kernel (k2_tc_bs)
+template <int KCH>
+static void run_tc_bs(Ctx &c, const TcPlanes &pl, const uint8_t *d_level_of, const char *name)
+{
+    const int NT = NVB_TC_NT, TM = NVB_TC_TM;
+    const int Kreal = pl.n_planes * c.P, Kpad = (Kreal + KCH - 1) / KCH * KCH, kchunks = Kpad / KCH;
+    int a_stages = nvb_tcbs_slots(kchunks, KCH);
+    if (getenv("TC_ASTAGES")) a_stages = atoi(getenv("TC_ASTAGES"));
+    if (a_stages < 2) { fprintf(stderr, "%s: rows too long for the resident view tile\n", name); return; }
+    const int smem = nvb_tcbs_smem(kchunks, a_stages, KCH);
+    int8_t *d_a, *d_b;
+    CK(cudaMalloc(&d_a, (size_t)c.G * Kpad));
+    CK(cudaMalloc(&d_b, (size_t)c.N * Kpad));
+    CK(cudaMemset(d_a, 0, (size_t)c.G * Kpad));
+    CK(cudaMemset(d_b, 0, (size_t)c.N * Kpad));
+    auto kern = k2_tc_bs<false, KCH>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const CUtensorMap ma = make_map(d_a, c.G, Kpad, KCH, TM), mb = make_map(d_b, c.N, Kpad, KCH, NT);
+    const int n_gt = (c.G + TM - 1) / TM, n_vt = (c.N + NT - 1) / NT;
+    const long long items = (long long)n_gt * n_vt;
+    const int n_cta = (int)std::min<long long>(c.sms, items);
+    std::vector<int> spans = make_spans(items, n_cta);
+    int *d_spans;
+    CK(cudaMalloc(&d_spans, sizeof(int) * spans.size()));
+    CK(cudaMemcpy(d_spans, spans.data(), sizeof(int) * spans.size(), cudaMemcpyHostToDevice));
+    TcArgs a{};
+    a.G = c.G; a.N = c.N; a.n_vt = n_vt; a.n_gt = n_gt; a.vt_major = 1; a.kchunks = kchunks; a.spans = d_spans; a.keys = c.d_keys;
+    a.view_offset = 0; a.sad_const = 0;
+    for (int k = 0; k < pl.n_planes; k++) a.sad_const += c.P * (int)pl.weight[k];
+    k_tc_encode<true><<<(unsigned)(((long long)c.G * c.P + 255) / 256), 256>>>(c.d_g, c.G, c.P, c.Ppad, Kpad, pl, d_level_of, d_a, (int *)(d_level_of + 512));
+    k_tc_encode<false><<<(unsigned)(((long long)c.N * c.P + 255) / 256), 256>>>(c.d_l, c.N, c.P, c.Ppad, Kpad, pl, d_level_of, d_b, (int *)(d_level_of + 512));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e9f, total = 0;
+    for (int r = 0; r < c.reps + 2; r++) {
+        k_fill<<<(c.G + 255) / 256, 256>>>(c.d_keys, c.G, NVB_KEY_NONE);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        kern<<<n_cta, NVB_TCBS_THREADS, smem>>>(ma, mb, a, a_stages);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        CK(cudaGetLastError());
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (r >= 2) { total += ms; best = std::min(best, ms); }
+    }
+    const bool ok = check(c, name);
+#if defined(NVB_TC_EXP_STAMPS)
+    {
+        long long *d_tl;
+        CK(cudaMalloc(&d_tl, sizeof(long long) * 32768));
+        CK(cudaMemset(d_tl, 0, sizeof(long long) * 32768));
+        TcArgs b = a;
+        b.tl = d_tl;
+        kern<<<n_cta, NVB_TCBS_THREADS, smem>>>(ma, mb, b, a_stages);
+        CK(cudaDeviceSynchronize());
+        std::vector<long long> h(8 * 64);
+        CK(cudaMemcpy(h.data(), d_tl + 20000, sizeof(long long) * 8 * 64, cudaMemcpyDeviceToHost));
+        const long long t0 = h[0];
+        fprintf(stderr, "%s: CTA 0, cycles since its first item: item | mma: inputs ready, MMAs issued, commits issued, - | epilogue: woke, released, folded\n", name);
+        for (int it = 0; it < 12 && h[it * 8] != 0; it++)
+            fprintf(stderr, "  %2d | loop top %6lld tempty ok %6lld | %6lld %6lld %6lld | %6lld %6lld %6lld\n", it, h[it * 8 + 3] - t0, h[it * 8 + 7] - t0, h[it * 8] - t0, h[it * 8 + 1] - t0, h[it * 8 + 2] - t0,
+                    h[it * 8 + 4] - t0, h[it * 8 + 5] - t0, h[it * 8 + 6] - t0);
+        cudaFree(d_tl);
+    }
+#endif
+    CK(cudaEventRecord(e0));
+    for (int r = 0; r < c.reps; r++) kern<<<n_cta, NVB_TCBS_THREADS, smem>>>(ma, mb, a, a_stages);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float b2b;
+    CK(cudaEventElapsedTime(&b2b, e0, e1));
+    const double ops = 2.0 * c.G * (double)c.N * Kreal;
+    printf("{\"kernel\": \"%s\", \"exact\": %s, \"us_mean\": %.2f, \"us_min\": %.2f, \"us_back_to_back\": %.2f, "
+           "\"items\": %lld, \"ctas\": %d, \"K\": %d, \"Kpad\": %d, \"a_stages\": %d, \"us_per_item_per_cta\": %.3f, \"tensor_TOPs\": %.1f}\n",
+           name, ok ? "true" : "false", total / c.reps * 1e3, best * 1e3, b2b / c.reps * 1e3, items, n_cta, Kreal, Kpad, a_stages,
+           b2b / c.reps * 1e3 / ((double)items / n_cta), ops / (b2b / c.reps * 1e-3) / 1e12);
+    fflush(stdout);
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_spans);
+}
+
 template <int TY, int MG, int MV, int CPR, int STAGES, bool BULK>
 static void run_simd(Ctx &c, const char *name)
 {
@@ -289,6 +370,13 @@ int main(int argc, char **argv)
         run_simd<16, 3, 15, 5, 3, true>(c, "k2_sad_v 48x240 (byte SIMD)");
         run_simd<16, 4, 16, 5, 3, true>(c, "k2_sad_v 64x256 (byte SIMD)");
     }
+#ifdef TC_EXP_NAME
+    run_tc_bs<64>(c, pl, d_level_of, "k2_tc_bs kch64 " TC_EXP_NAME);
+    run_tc_bs<128>(c, pl, d_level_of, "k2_tc_bs kch128 " TC_EXP_NAME);
+    return 0;
+#endif
+    run_tc_bs<64>(c, pl, d_level_of, "k2_tc_bs kch64 (view tile resident, tcgen05 i8)");
+    run_tc_bs<128>(c, pl, d_level_of, "k2_tc_bs kch128 (view tile resident, tcgen05 i8)");
     run_tc<64, 256, 8>(c, pl, d_level_of, "k2_tc kch64 nt256 s8 (tcgen05 i8)");
     run_tc<64, 240, 8>(c, pl, d_level_of, "k2_tc kch64 nt240 s8 (tcgen05 i8)");
     run_tc<128, 256, 4>(c, pl, d_level_of, "k2_tc kch128 nt256 s4 (tcgen05 i8)");
