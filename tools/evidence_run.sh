@@ -19,7 +19,7 @@ if [ $rc -eq 0 ]; then
   ncu --set full --clock-control none --import-source on -k regex:k2_ -s 40 -c 2 -f \
       -o $out/${tag}_k2 python bench.py --steps 20 --warmup 3 --quick --no-cpu > $out/${tag}_ncu2.log 2>&1
   echo "ncu k2 rc=$?"
-  ncu --set full --clock-control none --import-source on -k regex:k3_ -s 120 -c 3 -f \
+  ncu --set full --clock-control none --import-source on -k regex:k3_ -s 40 -c 2 -f \
       -o $out/${tag}_k3 python bench.py --steps 20 --warmup 3 --quick --no-cpu > $out/${tag}_ncu3.log 2>&1
   echo "ncu k3 rc=$?"
 fi

@@ -64,11 +64,11 @@ def main():
         step = {}
         for k, v in per.items():
             f.write("%-72s n=%4d mean=%8.2f us\n" % (k[:72], len(v), sum(v) / len(v)))
-            for key in ("k2", "k3_decide", "k3_ties", "k3_move_sample"):
-                if key in k:
+            for key in ("k2_tc", "k2_sad", "k3_decide", "k3_ties", "k3_move_sample", "k3_step_tm"):
+                if key in k and len(v) > 8:   # (the kernels of the steady-state step-batch, not the one-off first step)
                     step[key] = sum(v) / len(v)
         tot = sum(step.values())
-        f.write("\nsteady-state step-batch = " + " + ".join(step) + " = %.1f us under ncu\n" % tot)
+        f.write("\nkernels launched >= 8 times (steady-state step-batch and the roofline legs) = " + " + ".join(step) + " = %.1f us under ncu\n" % tot)
         f.write("shares: " + ", ".join("%s %.1f %%" % (k, 100 * v / tot) for k, v in step.items()) + "\n")
         r = bench["roofline"]
         f.write("bench.py (CUDA events, same build, no profiler): K2 %.1f us of a %.1f us L2-warm / %.1f us cold-L2 step-batch = %.1f %% / %.1f %%\n"
@@ -82,6 +82,7 @@ def main():
         f.write("(events around K2 in the eager timing pass include its launch latency, which the graph replay hides behind\n"
                 " the previous kernel; the k3 kernels gain more from a warm L2 than K2 does: hence the larger live share)\n")
     traffic = None
+    traffic_kernel = ""
     with open(os.path.join(PROF, tag + "_ncu_summary.txt"), "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on, C2 workload (bench.py --quick), one launch each\n")
         for rep in (tag + "_k2.ncu-rep", tag + "_k3.ncu-rep"):
@@ -95,13 +96,20 @@ def main():
                     if m in head:
                         i = head.index(m)
                         f.write("  %-72s %s %s\n" % (m, row[i], units[i]))
-                if "k2_sad_v" in row[head.index("Kernel Name")] and traffic is None:
+                name = row[head.index("Kernel Name")]
+                if "k2_tc" in name and traffic is None:
                     rd, wr = head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum")
                     traffic = float(row[rd]) * UNIT_SCALE[units[rd]] + float(row[wr]) * UNIT_SCALE[units[wr]]
+                    traffic_kernel = name.split("(")[0]
+                if ("k3_step_tm" in name or "k3_move_sample" in name) and "smsp__inst_executed.sum" in head:
+                    json.dump({"kernel": "k3_step_tm" if "k3_step_tm" in name else "k3_move_sample",
+                               "warp_instructions": float(row[head.index("smsp__inst_executed.sum")]),
+                               "source": "profiles/%s_ncu_summary.txt (ncu --set full, smsp__inst_executed.sum, one launch on C2)" % tag},
+                              open(os.path.join(PROF, "step_kernel_inst.json"), "w"))
     if traffic is not None:
         json.dump({"dram_bytes_per_launch": traffic,
                    "source": "profiles/%s_ncu_summary.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
-                             "one launch of k2_sad_v on C2)" % tag},
+                             "one launch of %s on C2, L2 flushed before the step)" % (tag, traffic_kernel)},
                   open(os.path.join(PROF, "k2_traffic.json"), "w"))
     for name in ("_bench_n1.json", "_bench_reference_arm.json"):
         shutil.copy(os.path.join(OUT, tag + name), os.path.join(PROF, tag + name))
