@@ -1752,6 +1752,16 @@ static int effective_form(const nvb_engine *e)
     return f;
 }
 
+// Grid-wide tie pass: one CTA per (tied glimpse, view chunk) for libraries that sit in L2, the
+// view-major form (library read once per launch) for large ones.
+static cudaError_t launch_ties(nvb_engine *e, const StepArgs &s)
+{
+    static const bool no_v = getenv("NAVSIM_B200_NO_TIES_V") != nullptr;
+    if (e->cw == 0.0 && e->Ppad <= 16 * NVB_TIEV_MAX_CHUNKS && (long long)e->N * e->Ppad > (8ll << 20) && !no_v)
+        return launch_seq(k3_ties_v, dim3(e->sm_count * 2), dim3(NVB_TIE_THREADS), 0, e->stream, s);
+    return launch_seq(k3_ties, dim3(e->sm_count * 2), dim3(NVB_TIE_THREADS), 0, e->stream, s);
+}
+
 template <bool HS, int PH, int PW>
 static int launch_k3ms_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa, size_t smem)
 {
@@ -1787,7 +1797,7 @@ static int launch_k3ms_t(nvb_engine *e, const StepArgs &s, const SamplerArgs &sa
         CK(launch_seq(k3_decide, dim3(e->B), dim3(NVB_STEP_THREADS), 0, e->stream, s));
         if (tev) cudaEventRecord(tev[1], e->stream);
         if (form == 3) {
-            CK(launch_seq(k3_ties, dim3(e->sm_count * 2), dim3(NVB_TIE_THREADS), 0, e->stream, s));
+            CK(launch_ties(e, s));
             e->launches += 1;
         }
         if (tev) cudaEventRecord(tev[2], e->stream);
@@ -1970,7 +1980,7 @@ static int one_step(nvb_engine *e, const StepArgs &s, bool sample_next = true)
         }
         if (step_form() >= 3) {   // decide | grid-wide tie pass | move, nothing sampled ahead
             CK(launch_seq(k3_decide, dim3(e->B), dim3(NVB_STEP_THREADS), 0, e->stream, s));
-            CK(launch_seq(k3_ties, dim3(e->sm_count * 2), dim3(NVB_TIE_THREADS), 0, e->stream, s));
+            CK(launch_ties(e, s));
             CK(launch_seq(k3_move, dim3(e->B), dim3(NVB_STEP_THREADS), 0, e->stream, s));
             e->launches += 3;
             return NVB_OK;

@@ -1214,6 +1214,65 @@ k3_ties(StepArgs a)
     nvb_tl_stamp(a.tl, 2, 2);
 }
 
+// Tie pass for LARGE libraries (chem_weight 0, rows of up to 128 bytes): view-major.  k3_ties
+// gives every (tied glimpse, 256-view chunk) pair to a CTA, so the library is read once PER tied
+// glimpse -- 80 MB each at 10^6 views, 350 us per step-batch with a dozen tied glimpses.  Here a
+// thread keeps ONE view row in registers and scores it against every tied glimpse (their rows
+// staged in shared memory, NVB_TIEV_ITEMS at a time): the library is read once per launch.
+#define NVB_TIEV_ITEMS 32
+#define NVB_TIEV_MAX_CHUNKS 8
+__global__ void __launch_bounds__(NVB_TIE_THREADS)
+k3_ties_v(StepArgs a)
+{
+    nvb_tl_stamp(a.tl, 2, 0);
+    if (a.pdl_early) nvb_grid_dep_launch();
+    nvb_grid_dep_wait();
+    nvb_tl_stamp(a.tl, 2, 1);
+    __shared__ uint4 s_q[NVB_TIEV_ITEMS][NVB_TIEV_MAX_CHUNKS];
+    __shared__ unsigned s_thr[NVB_TIEV_ITEMS];
+    __shared__ int s_g[NVB_TIEV_ITEMS];
+    const int n_items = *a.tie_count;
+    nvb_tl_stamp(a.tl, 2, 2);   // (overwritten below when there is work)
+    if (n_items == 0) return;
+    const int nc = a.Ppad / 16, tid = threadIdx.x;
+    for (int i0 = 0; i0 < n_items; i0 += NVB_TIEV_ITEMS) {
+        const int ni = min(NVB_TIEV_ITEMS, n_items - i0);
+        __syncthreads();   // the previous batch has been read
+        for (int q = tid; q < ni * nc; q += blockDim.x) {
+            const int i = q / nc, c = q - i * nc;
+            s_q[i][c] = reinterpret_cast<const uint4 *>(a.gv + (size_t)a.tie_items[i0 + i].x * a.Ppad)[c];
+        }
+        if (tid < ni) {
+            s_g[tid] = a.tie_items[i0 + tid].x;
+            const unsigned long long th = a.tie_thr[i0 + tid];
+            s_thr[tid] = th > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)th;
+        }
+        __syncthreads();
+        for (long long v = (long long)blockIdx.x * blockDim.x + tid; v < a.N; v += (long long)gridDim.x * blockDim.x) {
+            const uint4 *f4 = reinterpret_cast<const uint4 *>(a.lv + (size_t)v * a.Ppad);
+            uint4 row[NVB_TIEV_MAX_CHUNKS];
+#pragma unroll
+            for (int c = 0; c < NVB_TIEV_MAX_CHUNKS; c++)
+                if (c < nc) row[c] = __ldg(f4 + c);
+            for (int i = 0; i < ni; i++) {
+                uint32_t sum = 0;
+#pragma unroll
+                for (int c = 0; c < NVB_TIEV_MAX_CHUNKS; c++)
+                    if (c < nc) {
+                        const uint4 qq = s_q[i][c];
+                        sum = nvb_sad4(qq.x, row[c].x, sum); sum = nvb_sad4(qq.y, row[c].y, sum);
+                        sum = nvb_sad4(qq.z, row[c].z, sum); sum = nvb_sad4(qq.w, row[c].w, sum);
+                    }
+                if (sum <= s_thr[i]) {
+                    const double d = nvb_exact_diff_rows(a, (size_t)s_g[i] * a.Ppad, (size_t)v * a.Ppad, a.div255);
+                    atomicMin(a.exact + s_g[i], (unsigned long long)__double_as_longlong(d));
+                }
+            }
+        }
+    }
+    nvb_tl_stamp(a.tl, 2, 2);
+}
+
 __global__ void __launch_bounds__(NVB_STEP_THREADS)
 k3_move(StepArgs a)
 {
