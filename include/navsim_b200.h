@@ -248,7 +248,9 @@ int nvb_landscape_download(nvb_engine *e, uint8_t *hsv);
  * glimpses, else the byte-SIMD kernel; mode 1: the byte-SIMD kernel everywhere.  Both give
  * the same integer minima and view indices. */
 int nvb_set_distance_kernel(nvb_engine *e, int mode);
-/* 1 if the current agent batch is scored by the tensor-core kernel, else 0. */
+/* Which kernel scores the current agent batch: 1 = tensor cores (k2_tc / k2_tc_bs), 2 = the
+ * library-streaming byte-SIMD kernel for a handful of glimpses (k2_stream), 0 = the tiled
+ * byte-SIMD kernels (k2_sad_v, k2_sad_hsv_t). */
 int nvb_distance_kernel(nvb_engine *e);
 
 /* Test hook: sin and cos of n host doubles as the device-resident stepping loop computes

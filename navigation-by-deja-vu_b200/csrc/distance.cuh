@@ -21,6 +21,8 @@
 //
 // key = (score << idx_bits) | view_index     (lower is more familiar)
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 struct DistArgs {
@@ -324,6 +326,174 @@ k2_sad_v(DistArgs a)
             }
             if (++vt == a.n_vt) { vt = 0; gt++; }
         }
+    }
+    nvb_tl_stamp(a.tl, 0, 2);
+}
+
+// ---- few glimpses against a large library: the library streams through once --------------
+// One agent's heading sweep (G <= 16 glimpses) against 10^5 .. 10^7 views (BASELINE C4, and every
+// rank's slice of a view-sharded library): every library byte is read once and meets G glimpse
+// bytes -- 12.4 us of memory traffic per 10^6 views of 80 bytes and, for G = 10, 10.7 us of
+// VABSDIFF4 issue: both roofs at once.  k2_sad_v's CTA-wide tiles leave the SMs waiting there,
+// and its 10 x 256 tile spends more shared-memory bandwidth on broadcasting glimpse chunks than
+// the ALU pipe spends on SADs.  Here every WARP streams on its own: the library is cut into one
+// contiguous range of views per warp, a warp's lane 0 keeps NVB_STREAM_STAGES bulk copies
+// (cp.async.bulk, 128 views = 128 * 16 * CPR contiguous bytes each) in flight on per-warp
+// mbarriers -- no CTA-wide barrier, no producer warp -- and each lane scores FOUR views (rows
+// in registers, read from the stage with conflict-free LDS.128: odd CPR) against all glimpses
+// (rows in shared memory; one broadcast LDS.128 of a glimpse chunk now feeds 16 SADs: with two
+// views per lane the kernel was bound by shared-memory return bandwidth, 128 B/clk/SM, measured
+// in tools/micro/stream_probe.cu).  Per-thread running minima in registers; one shuffle
+// reduction and G atomicMin per CTA at the end.
+// Same keys as k2_sad_v: (sum << idx_bits) | global view index, lowest index among equal sums.
+#define NVB_STREAM_THREADS 128
+#define NVB_STREAM_STAGES 2
+#define NVB_STREAM_VPL 4     /* views per lane and chunk: one broadcast read of a glimpse chunk serves them all */
+#define NVB_STREAM_VPC (32 * NVB_STREAM_VPL)   /* views per chunk */
+#define NVB_STREAM_VBITS 17 /* a warp's range of views: index bits in the packed per-thread key */
+
+__host__ __device__ inline int nvb_stream_smem(int Ppad, int gmax)
+{
+    return (NVB_STREAM_THREADS / 32) * NVB_STREAM_STAGES * NVB_STREAM_VPC * Ppad + gmax * Ppad +
+           (NVB_STREAM_THREADS / 32) * gmax * 8 + (NVB_STREAM_THREADS / 32) * NVB_STREAM_STAGES * 8 + 128;
+}
+
+// EXACT: a.G == GMAX, no per-glimpse branch -- the SAD chains of different glimpses interleave (two
+// chains per glimpse alone leave the ALU pipe a third idle: measured, tools/micro/stream_probe.cu)
+template <int CPR, int GMAX, bool EXACT>
+__global__ void __launch_bounds__(NVB_STREAM_THREADS, 2)
+k2_stream(DistArgs a)
+{
+    constexpr int KC = 16 * CPR, NW = NVB_STREAM_THREADS / 32, ST = NVB_STREAM_STAGES, VPC = NVB_STREAM_VPC, VPL = NVB_STREAM_VPL;
+    constexpr int CHUNK = VPC * KC;
+    extern __shared__ __align__(128) uint8_t smem_st[];
+    uint8_t *stage0 = smem_st;                                              // [NW][ST][VPC][KC]
+    uint4 *s_q = reinterpret_cast<uint4 *>(smem_st + NW * ST * CHUNK);      // [GMAX][CPR]
+    unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(s_q + GMAX * CPR);   // [NW][GMAX]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_keys + NW * GMAX);      // [NW][ST]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *wstage = stage0 + (size_t)warp * ST * CHUNK;
+    uint64_t *wbar = bars + warp * ST;
+
+    nvb_tl_stamp(a.tl, 0, 0);
+    if (a.pdl_early) nvb_grid_dep_launch();
+    // this warp's views [v0, v1): equal shares of the library, to the view
+    const long long n_warps = (long long)gridDim.x * NW, gw = (long long)blockIdx.x * NW + warp;
+    const long long v0 = a.N * gw / n_warps, v1 = a.N * (gw + 1) / n_warps;
+    const int n_chunks = (int)((v1 - v0 + VPC - 1) / VPC);
+    auto issue = [&](int ch) {   // lane 0: chunk ch of this warp into its stage
+        const long long c0 = v0 + (long long)ch * VPC;
+        const uint32_t bytes = (uint32_t)(min((long long)VPC, v1 - c0) * KC);
+        uint64_t *bar = wbar + ch % ST;
+        nvb_mbar_expect_tx(bar, bytes);
+        nvb_bulk_load_1d(wstage + (size_t)(ch % ST) * CHUNK, a.lv + (size_t)c0 * KC, bytes, bar);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < ST; s++) nvb_mbar_init(wbar + s, 1);
+        nvb_fence_barrier_init();
+        // the library is not written by any kernel of the step sequence: first chunks now
+        for (int s = 0; s < ST && s < n_chunks; s++) issue(s);
+    }
+    nvb_grid_dep_wait();   // the glimpses are written by the previous kernel
+    nvb_tl_stamp(a.tl, 0, 1);
+    if (a.step_counter != nullptr && blockIdx.x == 0 && tid == 0) {
+        *a.step_counter += 1;
+        a.tie_count[0] = 0;
+        a.tie_count[1] = 0;
+        if (a.epoch != nullptr) *a.epoch += 1;
+    }
+    for (int q = tid; q < a.G * CPR; q += NVB_STREAM_THREADS) s_q[q] = reinterpret_cast<const uint4 *>(a.gv)[q];
+    __syncthreads();
+
+    // per-thread running minimum of (sum << NVB_STREAM_VBITS) | view index within this warp's range:
+    // sums stay below 2^15 (rows of up to 128 bytes), a warp's range below 2^17 views (the host checks)
+    uint32_t best[GMAX];
+#pragma unroll
+    for (int i = 0; i < GMAX; i++) best[i] = 0xFFFFFFFFu;
+
+    // FULL: all 64 rows of the chunk are views of this warp's range (every chunk but a ragged last one)
+    auto score = [&](int ch, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        nvb_mbar_wait(wbar + ch % ST, (uint32_t)((ch / ST) & 1));
+        const uint8_t *st = wstage + (size_t)(ch % ST) * CHUNK;
+        uint4 r[VPL][CPR];   // this lane's views: rows lane, lane + 32, ...
+#pragma unroll
+        for (int j = 0; j < VPL; j++)
+#pragma unroll
+            for (int c = 0; c < CPR; c++) r[j][c] = *reinterpret_cast<const uint4 *>(st + (size_t)(lane + 32 * j) * KC + 16 * c);
+        // every lane must HOLD its rows (not merely have requested them) before the stage is
+        // refilled through the async proxy: an instruction that consumes one register of every
+        // 16-byte load waits for them
+        uint32_t landed = 0;
+#pragma unroll
+        for (int j = 0; j < VPL; j++)
+#pragma unroll
+            for (int c = 0; c < CPR; c++) landed ^= r[j][c].x;
+        asm volatile("" ::"r"(landed) : "memory");
+        __syncwarp();
+        if (lane == 0 && ch + ST < n_chunks) issue(ch + ST);
+        const uint32_t lv0 = (uint32_t)(ch * VPC + lane);
+        const int rows = FULL ? VPC : (int)(v1 - (v0 + (long long)ch * VPC));
+#pragma unroll
+        for (int i = 0; i < GMAX; i++) {
+            if (EXACT || i < a.G) {
+                uint32_t sum[VPL];
+#pragma unroll
+                for (int j = 0; j < VPL; j++) sum[j] = 0;
+#pragma unroll
+                for (int c = 0; c < CPR; c++) {
+                    const uint4 q = s_q[i * CPR + c];   // one broadcast read serves VPL views
+#pragma unroll
+                    for (int j = 0; j < VPL; j++) sum[j] = nvb_sad4(q.x, r[j][c].x, sum[j]);
+#pragma unroll
+                    for (int j = 0; j < VPL; j++) sum[j] = nvb_sad4(q.y, r[j][c].y, sum[j]);
+#pragma unroll
+                    for (int j = 0; j < VPL; j++) sum[j] = nvb_sad4(q.z, r[j][c].z, sum[j]);
+#pragma unroll
+                    for (int j = 0; j < VPL; j++) sum[j] = nvb_sad4(q.w, r[j][c].w, sum[j]);
+                }
+                // keys on the FMA pipe (a true multiply-add), minima on the ALU pipe, which the SADs own
+                uint32_t k[VPL];
+#pragma unroll
+                for (int j = 0; j < VPL; j++) {
+                    k[j] = sum[j] * (1u << NVB_STREAM_VBITS) + (lv0 + 32u * j);
+                    if (!FULL) k[j] = (lane + 32 * j < rows) ? k[j] : 0xFFFFFFFFu;
+                }
+                uint32_t m = best[i];
+#pragma unroll
+                for (int j = 0; j + 1 < VPL; j += 2) m = __vimin3_u32(m, k[j], k[j + 1]);
+                if (VPL & 1) m = min(m, k[VPL - 1]);
+                best[i] = m;
+            }
+        }
+    };
+    const int n_full = (int)((v1 - v0) / VPC);
+    for (int ch = 0; ch < n_full; ch++) score(ch, std::true_type{});
+    if (n_full < n_chunks) score(n_full, std::false_type{});
+
+    // minimum over the lanes, then over the warps of the CTA, then one atomic per glimpse
+#pragma unroll
+    for (int i = 0; i < GMAX; i++) {
+        if (EXACT || i < a.G) {
+            uint32_t k = best[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) k = min(k, __shfl_xor_sync(0xFFFFFFFFu, k, o));
+            if (lane == 0) {
+                unsigned long long key = NVB_KEY_NONE;
+                if (k != 0xFFFFFFFFu)
+                    key = ((unsigned long long)(k >> NVB_STREAM_VBITS) << a.idx_bits) |
+                          (unsigned long long)(a.view_offset + v0 + (long long)(k & ((1u << NVB_STREAM_VBITS) - 1u)));
+                s_keys[warp * GMAX + i] = key;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < a.G) {
+        unsigned long long key = s_keys[tid];
+#pragma unroll
+        for (int w = 1; w < NW; w++) { const unsigned long long other = s_keys[w * GMAX + tid]; key = (other < key) ? other : key; }
+        if (key != NVB_KEY_NONE) atomicMin(a.keys + tid, key);
     }
     nvb_tl_stamp(a.tl, 0, 2);
 }

@@ -874,9 +874,46 @@ static int launch_dist_cfg(nvb_engine *e, const DistArgs &da)
     return launch_dist_cfg2<TY, MG, MV, CPR, BULK>(e, da);
 }
 
+// Few glimpses against a large library: every warp streams its own range of views (k2_stream).
+template <int CPR, int GMAX, bool EXACT>
+static int launch_stream(nvb_engine *e, const DistArgs &da)
+{
+    auto kern = k2_stream<CPR, GMAX, EXACT>;
+    const int smem = nvb_stream_smem(16 * CPR, GMAX);
+    static int occ_dev[64] = {0};
+    int &occ = occ_dev[e->device & 63];
+    if (occ == 0) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NVB_STREAM_THREADS, smem));
+        if (occ < 1) occ = 1;
+    }
+    // one wave; a warp wants at least a few chunks of 64 views
+    long long n_cta = (long long)e->sm_count * occ;
+    const long long want = (da.N + 4LL * NVB_STREAM_VPC * (NVB_STREAM_THREADS / 32) - 1) / (4LL * NVB_STREAM_VPC * (NVB_STREAM_THREADS / 32));
+    if (n_cta > want) n_cta = want;
+    if (n_cta < 1) n_cta = 1;
+    CK(launch_seq(kern, dim3((unsigned)n_cta), dim3(NVB_STREAM_THREADS), (size_t)smem, e->stream, da));
+    e->launches++;
+    CK(cudaGetLastError());
+    return NVB_OK;
+}
+
+static bool use_stream(const nvb_engine *e, const DistArgs &da)
+{
+    static const bool off = getenv("NAVSIM_B200_NO_STREAM") != nullptr;
+    // (a warp's range of views must fit the index bits of the kernel's packed per-thread key)
+    return !off && da.G <= 16 && e->nk == 1 && (e->cpr & 1) && da.N >= 16384 &&
+           da.N / ((long long)e->sm_count * (NVB_STREAM_THREADS / 32)) < (1 << NVB_STREAM_VBITS) - NVB_STREAM_VPC;
+}
+
 template <int CPR>
 static int launch_dist_cpr(nvb_engine *e, const DistArgs &da)
 {
+    if constexpr ((CPR & 1) != 0) if (use_stream(e, da)) {
+        if (da.G == 10) return launch_stream<CPR, 10, true>(e, da);   // the reference's default sweep
+        if (da.G < 10) return launch_stream<CPR, 10, false>(e, da);
+        return launch_stream<CPR, 16, false>(e, da);
+    }
     // few glimpses (one agent's heading sweep): G x 512 tiles, the library streams through
     // once; the row count is matched to the reference's default sweep of 10 headings
     if (da.G <= 10) return launch_dist_cfg<2, 5, 2, CPR>(e, da);       // 10 x 256 tiles, 4 stages in flight
@@ -1147,7 +1184,12 @@ extern "C" int nvb_set_distance_kernel(nvb_engine *e, int mode)
 
 extern "C" int nvb_distance_kernel(nvb_engine *e)
 {
-    if (e->B <= 0 || e->N <= 0 || !use_tc(e, (long long)e->B * e->A)) return 0;
+    if (e->B <= 0 || e->N <= 0) return 0;
+    if (!use_tc(e, (long long)e->B * e->A)) {
+        DistArgs da{};
+        da.G = e->B * e->A; da.N = e->N;
+        return (e->cw == 0.0 && use_stream(e, da)) ? 2 : 0;
+    }
     if (cudaSetDevice(e->device) != cudaSuccess) return 0;
     if (ensure_tc_library(e) != NVB_OK) return 0;
     return e->tc_lib_ok ? 1 : 0;

@@ -349,7 +349,8 @@ class NavEngine(object):
     @property
     def distance_kernel(self):
         """Name of the kernel that scores the current agent batch."""
-        return "k2_tc" if self._lib.nvb_distance_kernel(self._h) else ("k2_sad_hsv" if self.chem_weight else "k2_sad_v")
+        k = self._lib.nvb_distance_kernel(self._h)
+        return "k2_tc" if k == 1 else "k2_stream" if k == 2 else ("k2_sad_hsv" if self.chem_weight else "k2_sad_v")
 
     def kernel_time_ms(self):
         """(summed ms, launches) of the distance kernel since set_options(kernel_timing=True)."""

@@ -137,3 +137,32 @@ def test_chemistry_kernel_min_argmin(gpu, cw, W, H, G, N):
         assert md[g] == score.min() / 4096.0, (g, md[g], score.min() / 4096.0)
         assert vi[g] == int(np.argmin(score))
     assert md[0] == 0 and vi[0] == 3
+
+
+@pytest.mark.parametrize("W,H,G,N", [(40, 2, 10, 20000), (40, 2, 1, 16384), (40, 2, 16, 70001), (24, 2, 7, 33333),
+                                     (8, 2, 13, 100003), (56, 2, 10, 16385)])
+def test_streaming_kernel_few_glimpses_large_library(gpu, W, H, G, N):
+    """k2_stream (csrc/distance.cuh: a handful of glimpses, every warp streams its own range of the
+    library): minimum and LOWEST view index against NumPy, ragged ranges, duplicate views in
+    different warps' ranges, and the same keys as the tiled kernel."""
+    import navsim
+    rng = np.random.default_rng(W * 7919 + G * 31 + N)
+    L = np.zeros((64, 64, 3), np.uint8)
+    eng = navsim.NavEngine(L, (W, H), 1.0, n_test_angles=4, sensor_pixel_dimensions=(2, 2), n_sensor_levels=256)
+    scenes = np.zeros((N, H, W, 3), np.uint8)
+    scenes[..., 2] = rng.integers(0, 256, (N, H, W))
+    q = np.zeros((G, H, W, 3), np.uint8)
+    src = rng.integers(0, N, G)
+    q[..., 2] = scenes[src][..., 2]
+    noise = rng.random((G, H, W)) < 0.3
+    q[..., 2][noise] = rng.integers(0, 256, int(noise.sum()))
+    # exact duplicates of glimpse 0's best view far apart: the lowest index must win
+    for v in (17, N // 3, N - 1):
+        scenes[v] = q[0]
+    eng.set_library(scenes)
+    md, vi = eng.familiarity_min(q)
+    lib = scenes[..., 2].reshape(N, -1).astype(np.int32)
+    for g in range(G):
+        d = np.abs(lib - q[g, ..., 2].reshape(1, -1).astype(np.int32)).sum(axis=1)
+        assert md[g] == d.min() and vi[g] == int(np.argmin(d)), (g, md[g], vi[g], d.min(), int(np.argmin(d)))
+    assert md[0] == 0 and vi[0] == 17
