@@ -416,7 +416,7 @@ def run_ours(args):
                 "ms_per_step": t_e2e / K * 1e3, "agent_steps_per_sec": B * world * K / t_e2e,
                 "timing": "host perf_counter around K x (nvb_agents_step_io: poses from pinned host memory in, one "
                           "step-batch, heading / pose / familiarity into pinned host memory out, one stream "
-                          "synchronisation); the engine binds the caller's pinned buffers into the five kernels "
+                          "synchronisation); the engine binds the caller's pinned buffers into the three kernels "
                           "of the step (zero-copy reads and writes over the host link, no separate copy operations)",
                 "result_checksum": e2e_result_checksum},
         "gpu_launches": int(gpu_launches),

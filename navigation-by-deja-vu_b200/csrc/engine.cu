@@ -1696,6 +1696,7 @@ static StepArgs make_step_args(nvb_engine *e, int fake, int log_afam)
     s.pblk = getenv("NAVSIM_B200_NO_PATH_BLOCKS") ? nullptr : e->d_pblk;
     s.pblk2 = s.pblk ? e->d_pblk2 : nullptr;
     s.view_offset = e->view_offset;
+    s.no_sample = 0;
     s.keys = e->d_keys; s.exact = e->d_exact;
     s.idx_bits = (e->cw == 0.0) ? 32 : 28;
     s.band = (e->cw == 0.0) ? 0ull : 1ull;
@@ -2006,7 +2007,7 @@ static int one_step(nvb_engine *e, const StepArgs &s, bool sample_next = true)
 {
     int rc;
     // K2 leaves tile minima instead of packed keys only when k3_step_tm is what reads them
-    e->want_tmin = sample_next && fused_step(e) && split_step() && tm_form(e) && e->d_tmin != nullptr;
+    e->want_tmin = fused_step(e) && split_step() && tm_form(e) && e->d_tmin != nullptr;
     rc = phase1(e);
     const bool tm = e->want_tmin;
     e->want_tmin = false;
@@ -2019,6 +2020,11 @@ static int one_step(nvb_engine *e, const StepArgs &s, bool sample_next = true)
             if ((rc = split_step() ? launch_k3_split(e, s, tm) : launch_k31(e, s))) return rc;
             e->glimpses_pending = true;
             return NVB_OK;
+        }
+        if (tm) {   // the single-launch step without its gather: nothing sampled ahead
+            StepArgs s2 = s;
+            s2.no_sample = 1;
+            return launch_k3_split(e, s2, true);
         }
         if (step_form() >= 3) {   // decide | grid-wide tie pass | move, nothing sampled ahead
             CK(launch_seq(k3_decide, dim3(e->B), dim3(NVB_STEP_THREADS), 0, e->stream, s));
@@ -2034,6 +2040,13 @@ static int one_step(nvb_engine *e, const StepArgs &s, bool sample_next = true)
     }
     if ((rc = phase2(e, s))) return rc;
     return phase3(e, s);
+}
+
+// kernels in one host-driven step-batch (sample | distance | step kernels, nothing sampled ahead)
+static int io_step_launches(const nvb_engine *e)
+{
+    if (fused_step(e) && split_step() && tm_form(e) && e->d_tmin != nullptr) return 3;   // k1_sample | k2_tc* | k3_step_tm
+    return fused_step(e) && effective_form(e) < 3 ? 3 : 5;
 }
 
 static bool graph_valid(const nvb_engine *e, int fake, int log_afam)
@@ -2213,7 +2226,7 @@ extern "C" int nvb_agents_step_io(nvb_engine *e, const double *poses_in, int nst
         // the move writes the results into the caller's buffers
         CK(cudaGraphLaunch(e->graph_zc, e->stream));
         e->glimpses_pending = false;
-        e->launches += fused_step(e) && effective_form(e) < 3 ? 3 : 5;
+        e->launches += io_step_launches(e);
         e->steps_done += 1;
         CK(cudaStreamSynchronize(e->stream));
         return NVB_OK;
@@ -2252,7 +2265,7 @@ extern "C" int nvb_agents_step_io(nvb_engine *e, const double *poses_in, int nst
             e->graph_dirty = false;
         } else {
             CK(cudaGraphLaunch(e->graph_io, e->stream));
-            e->launches += fused_step(e) && effective_form(e) < 3 ? 3 : 5;
+            e->launches += io_step_launches(e);
             e->steps_done += 1;
         }
     } else if ((rc = run_steps(e, nsteps, 0, 0, poses_in != nullptr))) {

@@ -146,6 +146,7 @@ struct StepArgs {
     long long *dbg;              // tuning aid (see SamplerArgs::dbg), else nullptr
     unsigned long long *dmin2;   // [B] squared distance to the path (FP64 bits), long-path form
     int pdl_early;               // trigger the dependent launch at the top of every kernel
+    int no_sample;               // k3_step_tm: do not sample the next glimpses (host-driven calls: the host may move the agents first)
     long long *tl;               // tuning aid: timeline stamps (nvb_tl_stamp) or nullptr
     const double *pblk;          // [ceil(n_path / NVB_PATH_BLOCK)][4] bounding circles of path blocks, or nullptr
     const double *pblk2;         // [ceil(blocks / NVB_PATH_GROUP)][4] bounding circles of groups of blocks (long paths), or nullptr

@@ -440,7 +440,7 @@ k3_step_tm(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ste
         const double x = s_pose[0], y = s_pose[1];
         // the window of the next glimpses depends only on the new pose: its TMA loads fly during
         // the path scan; warp 1 computes the rotations meanwhile
-        const bool oob = nvb_sample_window<false>(&tmap, sa, b, x, y, L, 0, A);
+        const bool oob = a.no_sample ? true : nvb_sample_window<false>(&tmap, sa, b, x, y, L, 0, A);
         if (warp == 1) {
             if (!oob) nvb_sample_rotations(sa, b, s_pose[2], L, L.offs, 32, 32, 0, A);
         } else if (!a.fake) {
@@ -527,6 +527,10 @@ k3_step_tm(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ste
     }
     __syncthreads();   // rotations, s_more, the log's familiarities read the old glimpse rows
     nvb_tl_stamp(a.tl, 5, 0);
+    if (a.no_sample) {   // (no window in flight)
+        nvb_tl_stamp(a.tl, 3, 2);
+        return;
+    }
     const double x = s_pose[0], y = s_pose[1];
     const NvbWorld &w = sa.w;
     const bool oob = (x <= w.r || y <= w.r || x >= (double)w.cols - w.r || y >= (double)w.rows - w.r);
