@@ -242,6 +242,13 @@ int nvb_landscape_paint(nvb_engine *e, const uint8_t *H, const uint8_t *S, int64
 int nvb_landscape_flip(nvb_engine *e, int flip_v, int flip_h);
 int nvb_landscape_download(nvb_engine *e, uint8_t *hsv);
 
+/* Offline landscape generation, navsim.util.diffuse (navsim/util.pyx:186-235): nstep explicit
+ * time steps of the 2-D heat equation with periodic boundaries on a side x side float64 field,
+ *   new = m + multiplier * (m[i+1] + m[i-1] - 4 m + m[j+1] + m[j-1]),
+ * the reference's operation order without fused multiply-add (bit-identical).  The caller
+ * computes `multiplier` exactly as util.pyx:203-206 does.  Host pointers; out may alias initial. */
+int nvb_diffuse(nvb_engine *e, const double *initial, int64_t side, int64_t nstep, double multiplier, double *out);
+
 /* Which distance kernel scores the glimpses.  mode 0 (default): the tensor-core kernel
  * (tcgen05 int8, exact thermometer form of the sum of absolute differences) whenever the V
  * quantisation has at most 9 levels, chem_weight is 0 and the batch has at least 96

@@ -667,6 +667,30 @@ extern "C" int nvb_landscape_flip(nvb_engine *e, int flip_v, int flip_h)
     return rebuild_tmap(e);
 }
 
+extern "C" int nvb_diffuse(nvb_engine *e, const double *initial, int64_t side, int64_t nstep, double multiplier, double *out)
+{
+    if (!initial || !out || side <= 0 || side > 46340 || nstep < 0) return fail(NVB_E_INVALID, "diffuse: bad arguments");
+    CK(cudaSetDevice(e->device));
+    const size_t bytes = sizeof(double) * (size_t)side * side;
+    double *d_a = nullptr, *d_b = nullptr;
+    CK(cudaMalloc(&d_a, bytes));
+    if (cudaMalloc(&d_b, bytes) != cudaSuccess) { cudaFree(d_a); return fail(NVB_E_CUDA, "diffuse: out of device memory"); }
+    cudaError_t ce = cudaMemcpyAsync(d_a, initial, bytes, cudaMemcpyHostToDevice, e->stream);
+    const dim3 grid((unsigned)((side + 255) / 256), (unsigned)side);
+    for (int64_t t = 0; t < nstep && ce == cudaSuccess; t++) {
+        k_diffuse_step<<<grid, 256, 0, e->stream>>>(d_a, d_b, (int)side, multiplier);
+        e->launches++;
+        std::swap(d_a, d_b);
+        if ((t & 63) == 63) ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_a, bytes, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    cudaFree(d_a);
+    cudaFree(d_b);
+    if (ce != cudaSuccess) return fail(NVB_E_CUDA, "diffuse: %s", cudaGetErrorString(ce));
+    return NVB_OK;
+}
+
 extern "C" int nvb_landscape_download(nvb_engine *e, uint8_t *hsv)
 {
     if (!e->d_land) return fail(NVB_E_INVALID, "no landscape");

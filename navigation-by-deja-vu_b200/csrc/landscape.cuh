@@ -168,3 +168,22 @@ __global__ void k_ls_flip_planes(const uint8_t *src, int rows, int cols, int pit
     const int sy = flip_v ? rows - 1 - y : y, sx = flip_h ? cols - 1 - x : x;
     dst[pl * plane_stride + (size_t)y * pitch + x] = src[pl * plane_stride + (size_t)sy * pitch + sx];
 }
+
+// ---- offline landscape generation: diffuse (navsim/util.pyx:186-235) --------------------------
+// One explicit time step of the 2-D heat equation with periodic boundaries,
+//   new[i][j] = m[i][j] + multiplier * (m[i+1][j] + m[i-1][j] - 4 m[i][j] + m[i][j+1] + m[i][j-1]),
+// in the reference's operation order, no fused multiply-add: bit-identical to the Cython loop.
+// HBM/L2 bound (16 bytes per point and step; two 2000^2 fields stay in L2).
+__global__ void k_diffuse_step(const double *__restrict__ m, double *__restrict__ out, int side, double multiplier)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= side) return;
+    const int ip = (i + 1 == side) ? 0 : i + 1, im = (i == 0) ? side - 1 : i - 1;
+    const int jp = (j + 1 == side) ? 0 : j + 1, jm = (j == 0) ? side - 1 : j - 1;
+    const double c = m[(size_t)i * side + j];
+    double acc = __dadd_rn(m[(size_t)ip * side + j], m[(size_t)im * side + j]);   // util.pyx:218-219
+    acc = __dsub_rn(acc, __dmul_rn(4.0, c));                                       // :220
+    acc = __dadd_rn(acc, m[(size_t)i * side + jp]);                                // :221
+    acc = __dadd_rn(acc, m[(size_t)i * side + jm]);                                // :222
+    out[(size_t)i * side + j] = __dadd_rn(c, __dmul_rn(multiplier, acc));          // :216
+}

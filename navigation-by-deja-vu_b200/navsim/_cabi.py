@@ -32,6 +32,7 @@ SIGNATURES = {
     "nvb_landscape_grains_get": (_i, [_vp, _vp, _vp]),
     "nvb_landscape_paint": (_i, [_vp, _vp, _vp, _i64]),
     "nvb_landscape_flip": (_i, [_vp, _i, _i]),
+    "nvb_diffuse": (_i, [_vp, _vp, _i64, _i64, _d, _vp]),
     "nvb_landscape_download": (_i, [_vp, _vp]),
     "nvb_set_sensor": (_i, [_vp, _i, _i, _i, _i, _vp, _i]),
     "nvb_set_saccade": (_i, [_vp, _i, _vp]),

@@ -9,9 +9,10 @@ Hot-path functions (device):
     sads_familiarity   util.pyx:10-25  (closure over the library; kernel :28-73)
     downscale_chem     util.pyx:91-134
     fill_sensor_from   util.pyx:137-168
-Kept exported because the reference's drivers import them from here, but off
-the hot path and therefore plain host NumPy ("out of scope"):
-    set_HS_where_equal util.pyx:76-88, ssds :171-184, diffuse :186-235
+Off the hot path:
+    diffuse            util.pyx:186-235 (offline landscape generation; stencil kernel)
+    set_HS_where_equal util.pyx:76-88, ssds :171-184 (plain host NumPy; the batched driver paints
+                       chemistry on the device instead, nvb_landscape_paint)
 """
 import ctypes as C
 import math
@@ -179,11 +180,32 @@ def ssds(a_np, b_np):
 
 
 def diffuse(initial_condition, nstep, c=1.0, delta_t_factor=0.5):
-    """util.pyx:186-235: explicit 2-D heat equation, periodic boundaries."""
+    """util.pyx:186-235: explicit 2-D heat equation, periodic boundaries -- `nstep` stencil
+    passes on the device (nvb_diffuse), bit-identical to the Cython loop; same short circuit,
+    same sanity assertions."""
+    if nstep == 0:                                                       # :190-191
+        return initial_condition
+    initial_condition = np.asarray(initial_condition)
+    mat = np.ascontiguousarray(initial_condition, dtype=np.float64)     # :193
+    assert initial_condition.shape[0] == initial_condition.shape[1]     # :199
+    side = mat.shape[0]
+    delta_s = 1.0 / (side + 1)                                           # :202
+    delta_t = delta_t_factor * ((delta_s) ** 2 / (2 * c))                # :203
+    multiplier = c * (delta_t / (delta_s * delta_s))                     # :205
+    out = np.empty_like(mat)
+    check(_cabi.lib().nvb_diffuse(_engine(), ptr(mat), side, int(nstep), float(multiplier), ptr(out)))
+    assert np.sum(out) - np.sum(initial_condition) < 0.0000001           # :229-232
+    assert np.max(out) <= np.max(initial_condition)
+    assert np.min(out) >= np.min(initial_condition)
+    assert not np.any(np.isnan(out))
+    return out
+
+
+def diffuse_host(initial_condition, nstep, c=1.0, delta_t_factor=0.5):
+    """The same recurrence in NumPy (tests)."""
     if nstep == 0:
         return initial_condition
     mat = np.array(initial_condition, dtype=np.float64, copy=True)
-    assert mat.shape[0] == mat.shape[1]
     side = mat.shape[0]
     delta_s = 1.0 / (side + 1)
     delta_t = delta_t_factor * (delta_s ** 2 / (2 * c))

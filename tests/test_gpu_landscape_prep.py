@@ -83,3 +83,28 @@ def test_chemistry_and_flips_match_host(gpu):
     eng.set_world((40, 2), 5.0, n_test_angles=10, sensor_pixel_dimensions=(2, 4), chem_weight=0.3)
     assert eng.train_from_path(tpath) == ref.train_from_path(tpath) == (0, -1)
     assert np.array_equal(eng.familiar_scenes, ref.familiar_scenes)
+
+
+@pytest.mark.parametrize("side,nstep", [(16, 5), (101, 37), (256, 450), (7, 1), (64, 0)])
+def test_diffuse_bit_identical(gpu, side, nstep):
+    """navsim.util.diffuse (util.pyx:186-235, offline landscape generation) on the
+    device: bit-identical to the compiled reference's Cython loop (where oracle/_ref exists) and
+    to the NumPy restatement; same short circuit for nstep == 0."""
+    from navsim import util
+    rng = np.random.default_rng(side * 1000 + nstep)
+    m = rng.random((side, side))
+    if side == 101:
+        m = (rng.random((side, side)) < 0.3).astype(np.uint8)   # the generator's 0/1 images (generate_landscapes.py)
+    got = util.diffuse(m, nstep)
+    if nstep == 0:
+        assert got is m
+        return
+    assert got.dtype == np.float64 and got.shape == m.shape
+    assert np.array_equal(got, util.diffuse_host(m, nstep))
+    try:
+        from oracle import ref_loader
+        ref = ref_loader.load_reference()
+    except Exception:
+        ref = None
+    if ref is not None:
+        assert np.array_equal(got, ref.util.diffuse(m, nstep))

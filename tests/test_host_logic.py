@@ -63,4 +63,4 @@ def test_off_hot_path_util_matches_reference():
     x, y = rng.random((6, 7)), rng.random((6, 7))
     assert np.isclose(util.ssds(x, y), ref.util.ssds(x, y), rtol=1e-14)
     m = rng.random((16, 16))
-    assert np.allclose(util.diffuse(m, 5), ref.util.diffuse(m, 5), rtol=1e-12, atol=1e-15)
+    assert np.array_equal(util.diffuse_host(m, 5), ref.util.diffuse(m, 5))   # (the product's diffuse runs on the device: tests/test_gpu_landscape_prep.py)
