@@ -138,6 +138,7 @@ struct nvb_engine {
     int32_t *d_budget0 = nullptr;
     // CUDA graph of one step-batch (phase1+2+3), keyed on (fake, log_afam, log buffers)
     cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphExec_t graph_multi = nullptr;   // NVB_GRAPH_UNROLL step-batches in one graph (valid with graph_exec)
     cudaGraphExec_t graph_io = nullptr;   // one step-batch from fresh poses, nothing sampled ahead
     // the same without copy operations, for a caller that keeps passing the same page-locked
     // buffers: the sampler reads the poses from the host buffer and the move writes the results
@@ -520,6 +521,7 @@ extern "C" void nvb_engine_destroy(nvb_engine *e)
         if (e->p2p_opened[i]) cudaIpcCloseMemHandle(e->p2p_opened[i]);
     free_dev(e->d_xarea); free_dev(e->d_p2p_seq); free_dev(e->d_p2p_err);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->graph_multi) cudaGraphExecDestroy(e->graph_multi);
     if (e->graph_io) cudaGraphExecDestroy(e->graph_io);
     if (e->graph_zc) cudaGraphExecDestroy(e->graph_zc);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
@@ -2073,6 +2075,8 @@ static int io_step_launches(const nvb_engine *e)
     return fused_step(e) && effective_form(e) < 3 ? 3 : 5;
 }
 
+#define NVB_GRAPH_UNROLL 8
+
 static bool graph_valid(const nvb_engine *e, int fake, int log_afam)
 {
     return e->graph_exec && !e->graph_dirty && e->graph_fake == fake && e->graph_afam == log_afam &&
@@ -2085,6 +2089,7 @@ static int ensure_graph(nvb_engine *e, int fake, int log_afam)
 {
     if (graph_valid(e, fake, log_afam)) return NVB_OK;
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    if (e->graph_multi) { cudaGraphExecDestroy(e->graph_multi); e->graph_multi = nullptr; }
     if (e->graph_io) { cudaGraphExecDestroy(e->graph_io); e->graph_io = nullptr; }   // shares graph_dirty
     if (e->graph_zc) { cudaGraphExecDestroy(e->graph_zc); e->graph_zc = nullptr; }
     const StepArgs s = make_step_args(e, fake, log_afam);
@@ -2103,6 +2108,26 @@ static int ensure_graph(nvb_engine *e, int fake, int log_afam)
     e->graph_fake = fake; e->graph_afam = log_afam; e->graph_log_cap = e->log_cap; e->graph_B = e->B;
     e->graph_log_ptr = e->log_best;
     e->graph_dirty = false;
+    // Several step-batches in one graph: between graph launches the next kernel cannot become
+    // resident before the previous graph has drained, inside a graph the programmatic edges let
+    // the distance kernel's prologue (barriers, TMEM, first library tiles) overlap the step
+    // kernel's tail.  Steady-state steps are identical (device-side step counter), so the same
+    // capture repeated NVB_GRAPH_UNROLL times is NVB_GRAPH_UNROLL steps.  Not fatal if it fails.
+    static const bool no_multi = getenv("NAVSIM_B200_NO_MULTI_GRAPH") != nullptr;
+    if (fused_step(e) && !no_multi) {
+        graph = nullptr;
+        const bool pending = e->glimpses_pending;
+        if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            for (int i = 0; i < NVB_GRAPH_UNROLL && rc == NVB_OK; i++) rc = one_step(e, s);
+            ce = cudaStreamEndCapture(e->stream, &graph);
+            e->launches = before;
+            e->glimpses_pending = pending;
+            if (rc == NVB_OK && ce == cudaSuccess && cudaGraphInstantiate(&e->graph_multi, graph, 0) != cudaSuccess)
+                e->graph_multi = nullptr;
+            if (graph) cudaGraphDestroy(graph);
+        }
+        cudaGetLastError();
+    }
     return NVB_OK;
 }
 
@@ -2133,9 +2158,16 @@ static int run_steps(nvb_engine *e, int nsteps, int fake, int log_afam, bool eag
         const int ef = effective_form(e);
         const int per_step = fused_step(e) ? ((tm_form(e) && e->d_tmin && split_step()) ? 2 : ef == 3 ? 4 : (ef == 2 || ef == 4) ? 3 : 2)
                                            : 5 + (long_path_split(e) && !fake ? 2 : 0);
-        for (int i = done; i < nsteps; i++) {
-            CK(cudaGraphLaunch(e->graph_exec, e->stream));
-            e->launches += per_step;
+        for (int i = done; i < nsteps;) {
+            if (e->graph_multi && nsteps - i >= NVB_GRAPH_UNROLL) {
+                CK(cudaGraphLaunch(e->graph_multi, e->stream));
+                e->launches += per_step * NVB_GRAPH_UNROLL;
+                i += NVB_GRAPH_UNROLL;
+            } else {
+                CK(cudaGraphLaunch(e->graph_exec, e->stream));
+                e->launches += per_step;
+                i += 1;
+            }
         }
     } else {
         const StepArgs s = make_step_args(e, fake, log_afam);
@@ -2272,6 +2304,7 @@ extern "C" int nvb_agents_step_io(nvb_engine *e, const double *poses_in, int nst
             if (e->graph_io) { cudaGraphExecDestroy(e->graph_io); e->graph_io = nullptr; }
             if (e->graph_zc) { cudaGraphExecDestroy(e->graph_zc); e->graph_zc = nullptr; }   // same baked pointers
             if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+            if (e->graph_multi) { cudaGraphExecDestroy(e->graph_multi); e->graph_multi = nullptr; }
             const int64_t before = e->launches;
             cudaGraph_t graph = nullptr;
             CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
