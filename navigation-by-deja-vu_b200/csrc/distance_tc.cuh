@@ -62,6 +62,28 @@ struct TcArgs {
     long long *tl;
 };
 
+
+// Tuning aids: per-item stamps of the view-tile-stationary kernel.  NVB_TC_EXP_STAMPS (tools/micro/tc_sad.cu):
+// CTA 0, SM cycles; NVB_TC_SITU_STAMPS (tools/k2_situ.py builds a second library with it): every CTA, global
+// timer, into the unused decide rows of the engine's timeline buffer, to line up with the step kernels' stamps.
+#if defined(NVB_TC_SITU_STAMPS)
+#define NVB_TC_STAMP(it_, x_)                                                                          \
+    do {                                                                                               \
+        if (a.tl != nullptr && (it_) < 4) {                                                            \
+            long long t_;                                                                              \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                     \
+            a.tl[6144 + blockIdx.x * 32 + (it_) * 8 + (x_)] = t_;                                      \
+        }                                                                                              \
+    } while (0)
+#elif defined(NVB_TC_EXP_STAMPS)
+#define NVB_TC_STAMP(it_, x_)                                                                          \
+    do {                                                                                               \
+        if (a.tl != nullptr && blockIdx.x == 0 && (it_) < 60) a.tl[20000 + (it_) * 8 + (x_)] = clock64(); \
+    } while (0)
+#else
+#define NVB_TC_STAMP(it_, x_) do { } while (0)
+#endif
+
 // ---- PTX wrappers -----------------------------------------------------------------
 __device__ __forceinline__ void nvb_tma_load_2d(void *dst, const CUtensorMap *tmap, int x, int y, uint64_t *bar)
 {
@@ -253,6 +275,29 @@ __device__ __forceinline__ int2 nvb_tc_fold_item(uint32_t taddr, int nvalid, Rel
     nvb_tmem_wait_ld();
     release();
     nvb_tc_min64<TOP2>(rb, 192, nvalid, best, second);
+    return make_int2(best, second);
+}
+
+// The same for ONE HALF of the accumulator, columns [c0, c0 + 128) (taddr points at column 0):
+// two warps per TMEM lane quarter share an item (k2_tc_bs).
+template <bool TOP2, typename Release>
+__device__ __forceinline__ int2 nvb_tc_fold_half(uint32_t taddr, int c0, int nvalid, Release release)
+{
+    uint32_t ra[64], rb[64];
+    int best = 0x7FFFFFFF, second = 0x7FFFFFFF;
+#if defined(NVB_TC_EXP_NO_EPI_LD)   /* tools/micro experiments only */
+    release();
+    return make_int2((int)taddr, 0);
+#endif
+    // both loads in flight at once, one wait, and the accumulator goes back to the MMA warps before
+    // any folding: with two accumulator buffers the chain release -> MMA of the item after next ->
+    // its epilogue is what paces a CTA (tools/k2_situ.py)
+    nvb_tmem_ld64(taddr + (uint32_t)c0, ra);
+    nvb_tmem_ld64(taddr + (uint32_t)c0 + 64u, rb);
+    nvb_tmem_wait_ld();
+    release();
+    nvb_tc_min64<TOP2>(ra, c0, nvalid, best, second);
+    nvb_tc_min64<TOP2>(rb, c0 + 64, nvalid, best, second);
     return make_int2(best, second);
 }
 
@@ -451,7 +496,7 @@ k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensor
 // Shared memory: kchunks x NT x KCH (view tile) + a_slots x kchunks x TM x KCH (glimpse ring).
 #define NVB_TCBS_KCH 64
 #define NVB_TCBS_MAX_SLOTS 4
-#define NVB_TCBS_THREADS 224   /* producer, MMA issuer (even items), 4 epilogue warps, MMA issuer (odd items) */
+#define NVB_TCBS_THREADS 352   /* producer, MMA issuer (even items), 4 epilogue warps (columns 0..127), MMA issuer (odd items), 4 epilogue warps (columns 128..255) */
 
 __host__ __device__ inline int nvb_tcbs_smem(int kchunks, int a_slots, int kch = NVB_TCBS_KCH)
 {
@@ -460,7 +505,10 @@ __host__ __device__ inline int nvb_tcbs_smem(int kchunks, int a_slots, int kch =
 // glimpse slots that fit beside the view tile (at least 2 for the kernel to apply)
 __host__ __device__ inline int nvb_tcbs_slots(int kchunks, int kch = NVB_TCBS_KCH)
 {
-    const int s = (200 * 1024 - kchunks * NVB_TC_NT * kch) / (kchunks * NVB_TC_TM * kch);
+    // 227 KB per CTA less alignment slack, barriers and the kernel's static shared memory.  The
+    // glimpse rows of an item take ~1.5 us from request to landing (148 SMs ask at once) against
+    // 0.7 us of MMA: with two slots the kernel was paced by that latency (tools/k2_situ.py)
+    const int s = (227 * 1024 - 1024 - 256 - 4096 - kchunks * NVB_TC_NT * kch) / (kchunks * NVB_TC_TM * kch);
     return s > NVB_TCBS_MAX_SLOTS ? NVB_TCBS_MAX_SLOTS : s;
 }
 
@@ -494,7 +542,7 @@ k2_tc_bs(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUten
         nvb_mbar_init(bfull, 1);
         nvb_mbar_init(bempty, 3);   // both issuers have seen the tile + the epilogue has seen its last item complete
         nvb_mbar_init(tfull + 0, 1); nvb_mbar_init(tfull + 1, 1);
-        nvb_mbar_init(tempty + 0, 4); nvb_mbar_init(tempty + 1, 4);
+        nvb_mbar_init(tempty + 0, 8); nvb_mbar_init(tempty + 1, 8);
         nvb_fence_barrier_init();
         nvb_prefetch_tmap(&tm_a);
         nvb_prefetch_tmap(&tm_b);
@@ -525,6 +573,7 @@ k2_tc_bs(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUten
             if (!waited) {
                 nvb_grid_dep_wait();   // the glimpses are written by the previous kernel of the step sequence
                 nvb_tl_stamp(a.tl, 0, 1);
+                if (lane == 0) NVB_TC_STAMP(0, 3);
                 waited = true;
             }
             if (lane == 0) {
@@ -573,9 +622,7 @@ k2_tc_bs(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUten
                 nvb_mbar_wait(tempty + buf, tph ^ 1u);   // the epilogue has drained this buffer
                 nvb_mbar_wait(afull + s, ph);
                 nvb_tc_fence_after();
-#if defined(NVB_TC_EXP_STAMPS)   /* tools/micro experiments only */
-                if (a.tl != nullptr && blockIdx.x == 0 && it < 60) a.tl[20000 + it * 8 + 0] = clock64();
-#endif
+                NVB_TC_STAMP(it, 0);
                 const uint8_t *slot = smem_a + (size_t)s * slot_bytes;
                 for (int kc = 0; kc < a.kchunks; kc++) {
                     const uint64_t da = nvb_umma_desc<KCH>(slot + (size_t)kc * A_BYTES);
@@ -585,19 +632,21 @@ k2_tc_bs(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUten
                         nvb_umma_i8(tmem_base + (uint32_t)(buf * 256), da + (uint64_t)(2 * j), db + (uint64_t)(2 * j),
                                     idesc, (uint32_t)((kc | j) != 0));
                 }
-#if defined(NVB_TC_EXP_STAMPS)
-                if (a.tl != nullptr && blockIdx.x == 0 && it < 60) a.tl[20000 + it * 8 + 1] = clock64();
-#endif
+                NVB_TC_STAMP(it, 1);
                 nvb_umma_commit(tfull + buf);   // accumulator complete
-#if defined(NVB_TC_EXP_STAMPS)
-                if (a.tl != nullptr && blockIdx.x == 0 && it < 60) a.tl[20000 + it * 8 + 2] = clock64();
-#endif
+                NVB_TC_STAMP(it, 2);
             }
             __syncwarp();
         }
-    } else if (warp >= 2 && warp <= 5) {
-        // ---- epilogue: warp w may touch TMEM lanes 32 * (w % 4) .. + 31
-        const int ew = warp & 3;
+    } else if (warp >= 2) {
+        // ---- epilogue: warp w may touch TMEM lanes 32 * (w % 4) .. + 31.  TWO warps per lane quarter:
+        // warps 2..5 fold columns 0..127 of an item, warps 7..10 columns 128..255 (measured inside
+        // the step graph, tools/k2_situ.py: four warps folding 256 columns each took 0.9 - 1.5 us
+        // per item against 0.68 us of MMA -- the epilogue, not the tensor pipe, paced the kernel).
+        // Tile minima: the upper half hands its (best, runner-up) to the lower half through shared
+        // memory (double buffered like the accumulators), which merges and stores.
+        __shared__ int2 s_part[2][NVB_TC_TM];
+        const int ew = warp & 3, half = (warp >= 7) ? 1 : 0;
         const int row = ew * 32 + lane;
         int it = 0, s = 0;
         for (int u = u0; u < u1; u++, it++) {
@@ -614,27 +663,29 @@ k2_tc_bs(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUten
                 if (u + 1 < u1 && (u + 1) / a.n_gt != vt) nvb_mbar_arrive(bempty);
             }
             if (++s == a_slots) s = 0;
-#if defined(NVB_TC_EXP_STAMPS)
-            if (a.tl != nullptr && blockIdx.x == 0 && it < 60 && tid == 64) a.tl[20000 + it * 8 + 4] = clock64();
-#endif
+            if (tid == 64) NVB_TC_STAMP(it, 4);
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256);
             const int nvalid = min(NT, a.N - vt * NT);
-            // min over columns of -256 * dot + column
-            const int2 b2 = nvb_tc_fold_item<TILEMIN>(taddr, nvalid, [&]() {
+            // min over this half's columns of -256 * dot + column
+            int2 b2 = nvb_tc_fold_half<TILEMIN>(taddr, 128 * half, nvalid, [&]() {
                 nvb_tc_fence_before();
                 __syncwarp();
                 if (lane == 0) nvb_mbar_arrive(tempty + buf);
-#if defined(NVB_TC_EXP_STAMPS)
-                if (a.tl != nullptr && blockIdx.x == 0 && it < 60 && tid == 64) a.tl[20000 + it * 8 + 5] = clock64();
-#endif
+                if (tid == 64) NVB_TC_STAMP(it, 5);
             });
-#if defined(NVB_TC_EXP_STAMPS)
-            if (a.tl != nullptr && blockIdx.x == 0 && it < 60 && tid == 64) a.tl[20000 + it * 8 + 6] = clock64();
-#endif
-            const int g = gt * TM + row, best = b2.x;
+            if (tid == 64) NVB_TC_STAMP(it, 6);
+            const int g = gt * TM + row;
             if (TILEMIN) {
-                if (g < a.G) a.tmin[(size_t)g * a.n_vt + vt] = b2;
-            } else if (g < a.G && best != 0x7FFFFFFF) {
+                if (half) s_part[buf][row] = b2;
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps, once per item
+                if (!half) {
+                    const int2 o = s_part[buf][row];
+                    // the two smallest of {b2.x <= b2.y} and {o.x <= o.y}
+                    b2 = make_int2(min(b2.x, o.x), __vimin3_s32(max(b2.x, o.x), b2.y, o.y));
+                    if (g < a.G) a.tmin[(size_t)g * a.n_vt + vt] = b2;
+                }
+            } else if (g < a.G && b2.x != 0x7FFFFFFF) {
+                const int best = b2.x;
                 const int col = best & 255;
                 const int dot = -(best >> 8);
                 const unsigned long long sad = (unsigned long long)((a.sad_const - dot) >> 1);
