@@ -327,10 +327,14 @@ def run_ours(args):
             "launch_ms": k2_s * 1e3, "launch_ms_alone": k2_alone_ms, "launches_timed": k2_n,
             "launch_ms_in_graph": k2_graph_ms,
             "frac_in_graph": (ops / (k2_graph_ms * 1e-3) / 1e12) / peak if k2_graph_ms else None,
-            "why_not_higher": "C2 is 2.0 us of tensor work (480 items of 128 x 256 x 320 on 148 SMs: 3.24 per SM at "
-                              "0.68 us of MMA each) behind ~2.5 us of per-launch set-up (TMEM allocation, barriers, "
-                              "first TMA round trip) and one exposed epilogue; at_16x_agents is the same kernel on a "
-                              "problem that fills the machine",
+            "why_not_higher": "C2 is 2.0 us of tensor work (480 items of 128 x 256 x 320 on 148 SMs: 3.24 per SM, 4 on "
+                              "the busiest, 0.68 us of MMA each).  Per-CTA stamps inside the replayed graph "
+                              "(tools/k2_situ.py): glimpse rows land 1.3 us after the dependency is met, then one item "
+                              "every 1.0 - 1.5 us (two TMEM accumulators: MMA of item i+2 waits for the epilogue of item "
+                              "i to release its buffer), done 7.7 us after the dependency; launch_ms (events around an "
+                              "eager launch) adds the launch latency and the set-up (barriers, TMEM allocation, "
+                              "tensor-map fetch, library tile) that the graph overlaps with the previous kernel; "
+                              "at_16x_agents is the same kernel on a problem that fills the machine",
             "at_16x_agents": None if big is None else {
                 "agents": big["agents"], "launch_ms_alone": big["launch_ms_alone"],
                 "achieved": 16.0 * ops / (big["launch_ms_alone"] * 1e-3) / 1e12,
