@@ -90,12 +90,22 @@ def main():
             if not os.path.exists(path):
                 continue
             head, units, rows = raw_page(path)
+            # every metric of the capture, one line per metric (first launch): the summaries can be re-derived
+            with open(os.path.join(PROF, rep.replace(".ncu-rep", "_raw_metrics.csv")), "w") as g:
+                w = csv.writer(g)
+                w.writerow(["metric", "unit"] + ["launch_%d" % i for i in range(len(rows))])
+                for i, m in enumerate(head):
+                    w.writerow([m, units[i]] + [row[i] for row in rows])
+            stall = [m for m in head if m.startswith("smsp__average_warps_issue_stalled_") and m.endswith("_per_issue_active.ratio")]
             for row in rows:
                 f.write("\n== %s  (%s)\n" % (row[head.index("Kernel Name")], rep))
                 for m in METRICS:
                     if m in head:
                         i = head.index(m)
                         f.write("  %-72s %s %s\n" % (m, row[i], units[i]))
+                f.write("  warp stall reasons (warps stalled per issued instruction, largest first):\n")
+                for m, v in sorted(((m, float(row[head.index(m)] or 0)) for m in stall), key=lambda t: -t[1])[:8]:
+                    f.write("    %-40s %.3f\n" % (m[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")], v))
                 name = row[head.index("Kernel Name")]
                 if "k2_tc" in name and traffic is None:
                     rd, wr = head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum")
