@@ -505,10 +505,9 @@ __host__ __device__ inline int nvb_tcbs_smem(int kchunks, int a_slots, int kch =
 // glimpse slots that fit beside the view tile (at least 2 for the kernel to apply)
 __host__ __device__ inline int nvb_tcbs_slots(int kchunks, int kch = NVB_TCBS_KCH)
 {
-    // 227 KB per CTA less alignment slack, barriers and the kernel's static shared memory.  The
-    // glimpse rows of an item take ~1.5 us from request to landing (148 SMs ask at once) against
-    // 0.7 us of MMA: with two slots the kernel was paced by that latency (tools/k2_situ.py)
-    const int s = (227 * 1024 - 1024 - 256 - 4096 - kchunks * NVB_TC_NT * kch) / (kchunks * NVB_TC_TM * kch);
+    // (200 KB of the 227: measured on C2, a third glimpse slot -- 206 KB -- does not pay: the item
+    // period is set by the accumulator hand-over, not by the glimpse loads, tools/k2_situ.py)
+    const int s = (200 * 1024 - kchunks * NVB_TC_NT * kch) / (kchunks * NVB_TC_TM * kch);
     return s > NVB_TCBS_MAX_SLOTS ? NVB_TCBS_MAX_SLOTS : s;
 }
 

@@ -1006,7 +1006,9 @@ static int launch_tc_bs(nvb_engine *e, TcArgs ta)
 {
     auto kern = k2_tc_bs<TILEMIN>;
     const int kchunks = e->tc_Kpad / NVB_TCBS_KCH;
-    const int a_stages = nvb_tcbs_slots(kchunks);   // glimpse slots (whole items) beside the resident view tile
+    int a_stages = nvb_tcbs_slots(kchunks);   // glimpse slots (whole items) beside the resident view tile
+    static const int max_slots = getenv("NAVSIM_B200_TCBS_SLOTS") ? atoi(getenv("NAVSIM_B200_TCBS_SLOTS")) : 0;   // tuning knob
+    if (max_slots >= 2 && a_stages > max_slots) a_stages = max_slots;
     const int smem = nvb_tcbs_smem(kchunks, a_stages);
     static int attr_set[64] = {0};
     if (attr_set[e->device & 63] < smem) {
