@@ -278,26 +278,63 @@ __device__ __forceinline__ int2 nvb_tc_fold_item(uint32_t taddr, int nvalid, Rel
     return make_int2(best, second);
 }
 
+// nvb_tc_min64 for W columns
+template <bool TOP2, int W>
+__device__ __forceinline__ void nvb_tc_minw(const uint32_t (&r)[W], int c0, int nvalid, int &best, int &second)
+{
+    if (c0 + W <= nvalid) {
+#pragma unroll
+        for (int j = 0; j < W; j += 2) {
+            const int k1 = (int)r[j] * -256 + (c0 + j), k2 = (int)r[j + 1] * -256 + (c0 + j + 1);
+            if (TOP2) {
+                const int lo = min(k1, k2), hi = max(k1, k2);
+                second = __vimin3_s32(max(best, lo), second, hi);
+                best = min(best, lo);
+            } else {
+                best = __vimin3_s32(best, k1, k2);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; j++)
+            if (c0 + j < nvalid) {
+                const int k1 = (int)r[j] * -256 + (c0 + j);
+                if (TOP2) second = min(second, max(best, k1));
+                best = min(best, k1);
+            }
+    }
+}
+
 // The same for ONE HALF of the accumulator, columns [c0, c0 + 128) (taddr points at column 0):
-// two warps per TMEM lane quarter share an item (k2_tc_bs).
+// two warps per TMEM lane quarter share an item (k2_tc_bs).  Four loads of 32 columns through two
+// register buffers keep the kernel at ~104 registers per thread: with 352 threads that leaves room
+// on every SM sub-partition (register files are per sub-partition) for two CTAs of the step
+// kernel to become resident beside this one.  What that buys is launch work taken off the gap
+// between the kernels: the dependent grid's remaining CTAs are launched when this grid's CTAs
+// retire, and its dependency is released only after that burst (measured: gap = ~0.8 us + ~2.5 ns
+// per CTA still to launch; a 168-register version with both 64-column loads in flight finished
+// 0.5 us sooner and handed over 0.7 us later).  The accumulator goes back to the MMA warps as
+// soon as the last load has landed, before the last two folds.
 template <bool TOP2, typename Release>
 __device__ __forceinline__ int2 nvb_tc_fold_half(uint32_t taddr, int c0, int nvalid, Release release)
 {
-    uint32_t ra[64], rb[64];
+    uint32_t ra[32], rb[32];
     int best = 0x7FFFFFFF, second = 0x7FFFFFFF;
 #if defined(NVB_TC_EXP_NO_EPI_LD)   /* tools/micro experiments only */
     release();
     return make_int2((int)taddr, 0);
 #endif
-    // both loads in flight at once, one wait, and the accumulator goes back to the MMA warps before
-    // any folding: with two accumulator buffers the chain release -> MMA of the item after next ->
-    // its epilogue is what paces a CTA (tools/k2_situ.py)
-    nvb_tmem_ld64(taddr + (uint32_t)c0, ra);
-    nvb_tmem_ld64(taddr + (uint32_t)c0 + 64u, rb);
+    nvb_tmem_ld32(taddr + (uint32_t)c0, ra);
+    nvb_tmem_ld32(taddr + (uint32_t)c0 + 32u, rb);
+    nvb_tmem_wait_ld();
+    nvb_tc_minw<TOP2, 32>(ra, c0, nvalid, best, second);
+    nvb_tmem_ld32(taddr + (uint32_t)c0 + 64u, ra);
+    nvb_tc_minw<TOP2, 32>(rb, c0 + 32, nvalid, best, second);
+    nvb_tmem_ld32(taddr + (uint32_t)c0 + 96u, rb);
     nvb_tmem_wait_ld();
     release();
-    nvb_tc_min64<TOP2>(ra, c0, nvalid, best, second);
-    nvb_tc_min64<TOP2>(rb, c0 + 64, nvalid, best, second);
+    nvb_tc_minw<TOP2, 32>(ra, c0 + 64, nvalid, best, second);
+    nvb_tc_minw<TOP2, 32>(rb, c0 + 96, nvalid, best, second);
     return make_int2(best, second);
 }
 
@@ -496,6 +533,9 @@ k2_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensor
 // Shared memory: kchunks x NT x KCH (view tile) + a_slots x kchunks x TM x KCH (glimpse ring).
 #define NVB_TCBS_KCH 64
 #define NVB_TCBS_MAX_SLOTS 4
+#ifndef NVB_TCBS_MAXNREG
+#define NVB_TCBS_MAXNREG 112   /* 352 threads x 112 registers leave room for two step-kernel CTAs beside this one (see nvb_tc_fold_half) */
+#endif
 #define NVB_TCBS_THREADS 352   /* producer, MMA issuer (even items), 4 epilogue warps (columns 0..127), MMA issuer (odd items), 4 epilogue warps (columns 128..255) */
 
 __host__ __device__ inline int nvb_tcbs_smem(int kchunks, int a_slots, int kch = NVB_TCBS_KCH)
@@ -512,7 +552,7 @@ __host__ __device__ inline int nvb_tcbs_slots(int kchunks, int kch = NVB_TCBS_KC
 }
 
 template <bool TILEMIN, int KCH = NVB_TCBS_KCH>
-__global__ void __launch_bounds__(NVB_TCBS_THREADS, 1)
+__global__ void __maxnreg__(NVB_TCBS_MAXNREG)
 k2_tc_bs(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, TcArgs a, int a_slots)
 {
     constexpr int NT = NVB_TC_NT, TM = NVB_TC_TM;
