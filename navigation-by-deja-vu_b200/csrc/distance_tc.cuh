@@ -551,8 +551,10 @@ __host__ __device__ inline int nvb_tcbs_slots(int kchunks, int kch = NVB_TCBS_KC
     return s > NVB_TCBS_MAX_SLOTS ? NVB_TCBS_MAX_SLOTS : s;
 }
 
-template <bool TILEMIN, int KCH = NVB_TCBS_KCH>
-__global__ void __maxnreg__(NVB_TCBS_MAXNREG)
+// LEAN: few items per CTA -- 352 threads, eight register-lean epilogue warps (see nvb_tc_fold_half); else 224
+// threads, four epilogue warps
+template <bool TILEMIN, int KCH = NVB_TCBS_KCH, bool LEAN = true>
+__global__ void __maxnreg__(LEAN ? NVB_TCBS_MAXNREG : 168)
 k2_tc_bs(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, TcArgs a, int a_slots)
 {
     constexpr int NT = NVB_TC_NT, TM = NVB_TC_TM;
@@ -581,7 +583,7 @@ k2_tc_bs(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUten
         nvb_mbar_init(bfull, 1);
         nvb_mbar_init(bempty, 3);   // both issuers have seen the tile + the epilogue has seen its last item complete
         nvb_mbar_init(tfull + 0, 1); nvb_mbar_init(tfull + 1, 1);
-        nvb_mbar_init(tempty + 0, 8); nvb_mbar_init(tempty + 1, 8);
+        nvb_mbar_init(tempty + 0, LEAN ? 8 : 4); nvb_mbar_init(tempty + 1, LEAN ? 8 : 4);
         nvb_fence_barrier_init();
         nvb_prefetch_tmap(&tm_a);
         nvb_prefetch_tmap(&tm_b);
@@ -684,6 +686,9 @@ k2_tc_bs(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUten
         // per item against 0.68 us of MMA -- the epilogue, not the tensor pipe, paced the kernel).
         // Tile minima: the upper half hands its (best, runner-up) to the lower half through shared
         // memory (double buffered like the accumulators), which merges and stores.
+        // (not LEAN -- many items per CTA, launched with 224 threads: four epilogue warps fold the
+        // whole accumulator each, four pipelined 64-column loads, no merge: 0.83 us per item at
+        // 2000 items per CTA against 0.88 us for the eight-warp form)
         __shared__ int2 s_part[2][NVB_TC_TM];
         const int ew = warp & 3, half = (warp >= 7) ? 1 : 0;
         const int row = ew * 32 + lane;
@@ -706,15 +711,20 @@ k2_tc_bs(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUten
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256);
             const int nvalid = min(NT, a.N - vt * NT);
             // min over this half's columns of -256 * dot + column
-            int2 b2 = nvb_tc_fold_half<TILEMIN>(taddr, 128 * half, nvalid, [&]() {
+            auto release = [&]() {
                 nvb_tc_fence_before();
                 __syncwarp();
                 if (lane == 0) nvb_mbar_arrive(tempty + buf);
                 if (tid == 64) NVB_TC_STAMP(it, 5);
-            });
+            };
+            int2 b2;
+            if (LEAN) b2 = nvb_tc_fold_half<TILEMIN>(taddr, 128 * half, nvalid, release);
+            else b2 = nvb_tc_fold_item<TILEMIN>(taddr, nvalid, release);
             if (tid == 64) NVB_TC_STAMP(it, 6);
             const int g = gt * TM + row;
-            if (TILEMIN) {
+            if (TILEMIN && !LEAN) {
+                if (g < a.G) a.tmin[(size_t)g * a.n_vt + vt] = b2;
+            } else if (TILEMIN) {
                 if (half) s_part[buf][row] = b2;
                 asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps, once per item
                 if (!half) {

@@ -1001,10 +1001,10 @@ static int launch_tc_cfg(nvb_engine *e, TcArgs ta)
     return NVB_OK;
 }
 
-template <bool TILEMIN>
-static int launch_tc_bs(nvb_engine *e, TcArgs ta)
+template <bool TILEMIN, bool LEAN>
+static int launch_tc_bs_v(nvb_engine *e, TcArgs ta)
 {
-    auto kern = k2_tc_bs<TILEMIN>;
+    auto kern = k2_tc_bs<TILEMIN, NVB_TCBS_KCH, LEAN>;
     const int kchunks = e->tc_Kpad / NVB_TCBS_KCH;
     int a_stages = nvb_tcbs_slots(kchunks);   // glimpse slots (whole items) beside the resident view tile
     static const int max_slots = getenv("NAVSIM_B200_TCBS_SLOTS") ? atoi(getenv("NAVSIM_B200_TCBS_SLOTS")) : 0;   // tuning knob
@@ -1036,10 +1036,21 @@ static int launch_tc_bs(nvb_engine *e, TcArgs ta)
     ta.vt_major = 1;
     ta.kchunks = kchunks;
     ta.spans = e->d_spans_tc;
-    CK(launch_seq(kern, dim3((unsigned)n_cta), dim3(NVB_TCBS_THREADS), (size_t)smem, e->stream, e->tm_genc, e->tm_lenc, ta, a_stages));
+    CK(launch_seq(kern, dim3((unsigned)n_cta), dim3(LEAN ? NVB_TCBS_THREADS : 224), (size_t)smem, e->stream, e->tm_genc, e->tm_lenc, ta, a_stages));
     e->launches++;
     CK(cudaGetLastError());
     return NVB_OK;
+}
+
+// few items per CTA: the register-lean epilogue (step-kernel CTAs fit beside the kernel); many: the
+// epilogue with both halves of its columns in flight
+template <bool TILEMIN>
+static int launch_tc_bs(nvb_engine *e, TcArgs ta)
+{
+    const long long items = (long long)((ta.G + NVB_TC_TM - 1) / NVB_TC_TM) * ((ta.N + NVB_TC_NT - 1) / NVB_TC_NT);
+    static const int forced = getenv("NAVSIM_B200_TCBS_LEAN") ? atoi(getenv("NAVSIM_B200_TCBS_LEAN")) : -1;   // tuning knob
+    const bool lean = forced >= 0 ? forced != 0 : items <= 8LL * e->sm_count;
+    return lean ? launch_tc_bs_v<TILEMIN, true>(e, ta) : launch_tc_bs_v<TILEMIN, false>(e, ta);
 }
 
 // K2 on the tensor cores.  encode_glimpses: the glimpse planes were not written by the sampler
