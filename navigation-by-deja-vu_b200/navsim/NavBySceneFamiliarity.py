@@ -302,11 +302,79 @@ class NavBySceneFamiliarity(object):
         if np.linalg.norm(self.training_path[-1] - self._position) <= self.threshold_factor * self.step_size:
             raise ReachedEndOfTrainingPathException()
 
-    # ---- visualisation: out of scope -----------------------------------------
+    # ---- visualisation -------------------------------------------------------
+    # The reference's plotting methods (NavBySceneFamiliarity.py:333-661: _plot_landscape,
+    # compass_plot, animate) are matplotlib code that only reads public state this class has
+    # as well (position, angle, angle_familiarity, scene_familiarity, angle_offsets,
+    # training_path, sensor geometry, step_forward, the error properties).  They are not
+    # rebuilt here; a user who has the reference installed lends them to this navigator:
+    #     viz = nsf.plotting(reference_navsim.NavBySceneFamiliarity)
+    #     (fig, ax), stopped_for, path = viz.compass_plot(frames=40, show_navpath=True)
+    # and every frame they draw is stepped by the device-resident loop.
+    @property
+    def _landscape_rgb(self):
+        """RGB view of the HSV landscape for imshow (NavBySceneFamiliarity.py:74), made on first use."""
+        rgb = self.__dict__.get("_landscape_rgb_cache")
+        if rgb is None:
+            from PIL import Image
+            rgb = np.asarray(Image.fromarray(np.ascontiguousarray(self.landscape), mode='HSV').convert('RGB'))
+            self.__dict__["_landscape_rgb_cache"] = rgb
+        return rgb
+
+    def plotting(self, reference_class):
+        """The reference class's visualisation methods bound to this navigator (see above).
+        `reference_class` is the reference's NavBySceneFamiliarity; stop exceptions raised by
+        step_forward() reach its code as the reference's own exception classes."""
+        return _ReferencePlotting(self, reference_class)
+
     def _plot_landscape(self, *a, **k):
-        raise NotImplementedError("plotting is out of scope of the B200 hot-path build (DESIGN.md)")
+        raise NotImplementedError("plotting lives in the reference: use nsf.plotting(reference_class) "
+                                  "(matplotlib is needed; DESIGN.md, SURVEY 8(f) N4)")
 
     compass_plot = animate = _plot_landscape
+
+
+class _ReferencePlotting(object):
+    """Proxy handed to the reference's plotting functions as `self`: attribute reads and writes
+    go to the navigator, the three plotting methods come from the reference class, and
+    step_forward() translates this package's stop exceptions into the reference module's classes of
+    the same name (its `except StopNavigationException` clauses would not match ours)."""
+
+    _METHODS = ("_plot_landscape", "compass_plot", "animate")
+
+    def __init__(self, nsf, reference_class):
+        import sys
+        object.__setattr__(self, "_nsf", nsf)
+        ref_globals = None
+        for name in self._METHODS:
+            fn = getattr(reference_class, name)
+            fn = getattr(fn, "__func__", fn)
+            object.__setattr__(self, "_fn_" + name, fn)
+            if ref_globals is None:
+                ref_globals = getattr(fn, "__globals__", None)   # the namespace its `except` clauses look names up in
+        if ref_globals is None:
+            mod = sys.modules.get(getattr(reference_class, "__module__", ""), None)
+            ref_globals = vars(mod) if mod is not None else {}
+        object.__setattr__(self, "_ref_globals", ref_globals)
+
+    def __getattr__(self, name):
+        if name in _ReferencePlotting._METHODS:
+            fn = object.__getattribute__(self, "_fn_" + name)
+            return lambda *a, **k: fn(self, *a, **k)
+        return getattr(object.__getattribute__(self, "_nsf"), name)
+
+    def __setattr__(self, name, value):
+        setattr(object.__getattribute__(self, "_nsf"), name, value)
+
+    def step_forward(self, fake=False):
+        nsf = object.__getattribute__(self, "_nsf")
+        try:
+            return nsf.step_forward(fake)
+        except StopNavigationException as e:
+            ref_exc = object.__getattribute__(self, "_ref_globals").get(type(e).__name__)
+            if ref_exc is None or ref_exc is type(e):
+                raise
+            raise ref_exc() from e
 
 
 class _FamiliarityFunc(object):

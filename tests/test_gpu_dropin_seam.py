@@ -188,3 +188,59 @@ def test_dropin_parameters_changed_mid_run(gpu):
         nsf.step_forward()
     assert nsf.position == (ag.x, ag.y) and nsf.navigated_for_frames == ag.navigated_for_frames
     assert nsf.replay_restarts == 0
+
+
+def test_reference_plotting_methods_run_on_the_product(gpu):
+    """the reference's compass_plot / _plot_landscape (NavBySceneFamiliarity.py:333-473,
+    matplotlib code that only reads public navigator state) lent to the product's navigator through
+    nsf.plotting(reference_class): every frame is stepped by the device-resident loop, the path they
+    return equals a plain run, a stop reaches their `except StopNavigationException` as the
+    reference's own class.  matplotlib is absent here: the reference module's plotting globals are
+    mocks that only record calls."""
+    from unittest import mock
+    import navsim
+    from oracle import ref_loader
+    ref = ref_loader.load_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (reference sources absent when build() ran)")
+    L, w, tpath, pose, frames = build_case("c1_small")
+    kw = dict(w)
+    kw.pop("chem_weight", None)
+
+    def make():
+        nsf = navsim.NavBySceneFamiliarity(L, sensor_px_per_mm=2.0, **kw)
+        nsf.train_from_path(tpath)
+        nsf.position = (pose[0], pose[1])
+        nsf.angle = pose[2]
+        return nsf
+
+    plain = make()
+    want = [tuple(plain.position)]
+    for _ in range(12):
+        plain.step_forward()
+        want.append(tuple(plain.position))
+
+    nsf = make()
+    viz = nsf.plotting(ref.NavBySceneFamiliarity)
+    ax = mock.MagicMock()
+    ax.plot.return_value = [mock.MagicMock()]   # `path_ln, = main_ax.plot(...)`, NavBySceneFamiliarity.py:463
+    names = ("plt", "matplotlib", "fm", "AnchoredSizeBar")
+    with mock.patch.multiple(ref.module, **{n: mock.MagicMock() for n in names if hasattr(ref.module, n)}):
+        (fig, main_ax), stopped_for, path = viz.compass_plot(ax=ax, frames=12, show_every=3, show_navpath=True)
+    assert fig is None and main_ax is ax and stopped_for is None
+    assert np.array_equal(path, np.array(want))
+    assert ax.imshow.call_count == 1 and ax.imshow.call_args[0][0].shape == L.shape   # the RGB landscape
+    assert ax.add_patch.call_count == 8 and ax.arrow.call_count == 4                  # frames 0, 3, 6, 9
+    assert np.array_equal(nsf.position, plain.position) and nsf.angle == plain.angle
+
+    # a navigator that stops: too far from the training path after a few frames
+    far = navsim.NavBySceneFamiliarity(L, max_distance_to_training_path=1.0, **{k: v for k, v in kw.items()
+                                                                              if k != "max_distance_to_training_path"})
+    far.train_from_path(tpath)
+    far.position = (pose[0] + 30.0, pose[1] + 30.0)
+    far.angle = pose[2]
+    with mock.patch.multiple(ref.module, **{n: mock.MagicMock() for n in names if hasattr(ref.module, n)}):
+        _, stopped_for, path = far.plotting(ref.NavBySceneFamiliarity).compass_plot(ax=mock.MagicMock(), frames=5,
+                                                                                   show_scalebar=False)
+    assert isinstance(stopped_for, ref.StopNavigationException) and stopped_for.get_code() == -1
+    assert len(path) == 2
