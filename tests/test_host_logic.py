@@ -64,3 +64,54 @@ def test_off_hot_path_util_matches_reference():
     assert np.isclose(util.ssds(x, y), ref.util.ssds(x, y), rtol=1e-14)
     m = rng.random((16, 16))
     assert np.array_equal(util.diffuse_host(m, 5), ref.util.diffuse(m, 5))   # (the product's diffuse runs on the device: tests/test_gpu_landscape_prep.py)
+
+
+def test_reference_plotting_proxy_mechanics():
+    """nsf.plotting(reference_class) without a device: the proxy hands the
+    reference's plotting functions this navigator's state, forwards attribute writes, and turns the
+    package's stop exceptions into the classes the reference's `except` clauses look up in their own
+    module namespace (the GPU test runs the compiled reference's real compass_plot this way)."""
+    from navsim.NavBySceneFamiliarity import (_ReferencePlotting, StopNavigationException,
+                                              TooFarFromTrainingPathException)
+
+    class RefStop(Exception):
+        pass
+
+    class RefTooFar(RefStop):
+        pass
+
+    ns = {"StopNavigationException": RefStop, "TooFarFromTrainingPathException": RefTooFar}
+    exec("def _plot_landscape(self, ax, training_path=True):\n"
+         "    ax.append(('landscape', self.position, self.training_path is not None and training_path))\n"
+         "def compass_plot(self, ax=None, frames=3):\n"
+         "    self._plot_landscape(ax)\n"
+         "    self._anim_stop_cond = False\n"
+         "    stopped = None\n"
+         "    for i in range(frames):\n"
+         "        try:\n"
+         "            self.step_forward()\n"
+         "        except StopNavigationException as e:\n"
+         "            stopped = e\n"
+         "            break\n"
+         "    return ax, stopped, self.position\n"
+         "def animate(self, frames):\n"
+         "    return frames\n", ns)
+    Ref = type("NavBySceneFamiliarity", (), {k: ns[k] for k in ("_plot_landscape", "compass_plot", "animate")})
+
+    class Nsf(object):
+        def __init__(self):
+            self.position, self.training_path, self.n = (0.0, 0.0), [1], 0
+
+        def step_forward(self, fake=False):
+            self.n += 1
+            self.position = (float(self.n), 0.0)
+            if self.n == 3:
+                raise TooFarFromTrainingPathException()
+
+    nsf = Nsf()
+    viz = _ReferencePlotting(nsf, Ref)
+    ax, stopped, pos = viz.compass_plot(ax=[], frames=5)
+    assert ax == [("landscape", (0.0, 0.0), True)]
+    assert type(stopped) is RefTooFar and isinstance(stopped.__cause__, StopNavigationException)
+    assert nsf.n == 3 and pos == (3.0, 0.0) and nsf._anim_stop_cond is False
+    assert viz.animate(7) == 7 and viz.n == 3
