@@ -40,6 +40,25 @@ def test_trial_grid_and_csv_format():
     assert row.endswith("17, 3, 0.500000, 0.750000, 1.250000, -2")
 
 
+@pytest.mark.parametrize("world_size", [1, 2, 3, 4, 8, 16])
+def test_worlds_split_over_ranks_is_a_partition(world_size):
+    """Multi-GPU sweeps: every world -- the trials that become the agents of one
+    engine batch -- goes to exactly one rank, in order, no collective; shares are balanced by trial
+    count to within one world; every trial of the grid is run by exactly one rank."""
+    from navsim import experiments as X
+    variables, trials = X.expand_trials(GRID)
+    worlds = X.group_worlds(trials)
+    assert sorted(i for _, ix in worlds for i in ix) == list(range(len(trials)))
+    for _, ix in worlds:      # a world = same everything but the start offset
+        assert len({tuple(sorted((k, str(v)) for k, v in trials[i].items() if k != "start_offset")) for i in ix}) == 1
+    shares = [X.split_worlds(worlds, world_size, r) for r in range(world_size)]
+    assert sum(shares, []) == worlds                               # contiguous, ordered, complete, disjoint
+    counts = [sum(len(ix) for _, ix in sh) for sh in shares]
+    biggest = max(len(ix) for _, ix in worlds)
+    assert max(counts) - min(counts) <= 2 * biggest or world_size > len(worlds)
+    assert sum(counts) == len(trials)
+
+
 @pytest.mark.gpu
 def test_sweep_matches_oracle_trial_by_trial(gpu, tmp_path):
     from navsim import experiments as X, synthetic
